@@ -1,0 +1,163 @@
+/* recmv_b200.h -- C ABI of the B200-native REC-MV hot path (librecmv_b200.so).
+ *
+ * Every entry point takes raw DEVICE pointers (unless a parameter says "host"), plain sizes and a
+ * cudaStream_t passed as void*.  No torch types.  Return value: 0 = ok, negative = argument error
+ * (RECMV_E_*), positive = cudaError_t raised by the launch.  Nothing here allocates result storage
+ * of data-dependent size: marching cubes is a count call followed by an emit call.  All kernels run
+ * on the caller's stream and never synchronise the device, except recmv_mc_count (it has to return
+ * two integers to the host, like the reference's blocking cudaMemcpy at MCGpu/CudaKernels.cu:628).
+ *
+ * Each block cites the reference interface (path:line under /root/reference) it replaces.
+ */
+#ifndef RECMV_B200_H_
+#define RECMV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* recmv_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define RECMV_API __attribute__((visibility("default")))
+#else
+#define RECMV_API
+#endif
+
+enum {
+  RECMV_OK = 0,
+  RECMV_E_NULL = -1,      /* required pointer is NULL            */
+  RECMV_E_DTYPE = -2,     /* dtype / layout / mode flag unknown  */
+  RECMV_E_SHAPE = -3,     /* non-positive or inconsistent extent */
+  RECMV_E_RANGE = -4,     /* size exceeds an implementation limit (e.g. > 2^26 MC vertices) */
+  RECMV_E_UNSUPPORTED = -5
+};
+
+enum { RECMV_F32 = 0, RECMV_F64 = 1 };
+enum { RECMV_LAYOUT_NCDHW = 0, RECMV_LAYOUT_NDHWC = 1 };
+
+/* SDF-MLP arithmetic.  All modes accumulate in fp32.
+ *   FP32_SIMT : fp32 FMA on CUDA cores (exact-fp32 verification mode, slow)
+ *   TC_F16X3  : tcgen05 kind::f16, operands split a = hi + lo (fp16 each), 3 MMAs per product
+ *               (hi*hi + lo*hi + hi*lo) -> ~2^-21 relative per product; meets the 1e-4 parity bar
+ *   TC_F16X1  : tcgen05 kind::f16 single pass (11-bit operands, like the TF32 the reference ran
+ *               with on Ampere); ~1e-3, NOT parity grade                                          */
+enum { RECMV_MLP_FP32_SIMT = 0, RECMV_MLP_TC_F16X3 = 1, RECMV_MLP_TC_F16X1 = 2 };
+
+RECMV_API int recmv_version(void);
+RECMV_API const char* recmv_error_string(int status);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+RECMV_API int64_t recmv_launch_count(void);
+
+/* ---- A6: FastMinv.Fast3x3Minv / Fast3x3Minv_backward --------------------------------------
+ * replaces FastMinv/M3x3Inv.cpp:12-59 (pybind) + Matrix3x3InvKernels.cu:21-142.
+ * ms/invs/grads/outs: [n,3,3] contiguous; ok: [n] bytes (1 = invertible, |det| >= 1e-4).        */
+RECMV_API int recmv_minv3x3_fwd(const void* ms, void* invs, uint8_t* ok, int64_t n, int dtype,
+                      recmv_stream_t stream);
+RECMV_API int recmv_minv3x3_bwd(const void* grads, const void* invs, void* outs, int64_t n, int dtype,
+                      recmv_stream_t stream);
+
+/* ---- K4-K6: GridSamplerMine.forward / backward / dbackward --------------------------------
+ * replaces MCAcc/cuda/GridSamplerMine.cpp:75-103 + GridSamplerMineKernel.cu:160-1022.
+ * trilinear, border padding, align_corners=False.  input [N,C,D,H,W] (layout NCDHW) or
+ * [N,D,H,W,C] (NDHWC, the coalesced internal layout); grid [N,P,3] (x->W, y->H, z->D);
+ * output / grad_out / gg_out [N,C,P].
+ * bwd : grad_input may be NULL (skipped -- the skinning voxel is a frozen buffer); otherwise it
+ *       must be zero-filled by the caller and has the layout of `input`.
+ * bwd2: cotangents gg_input (layout of input, may be NULL = zeros) and gg_grid [N,P,3];
+ *       outputs g_input (may be NULL; else zero-filled), g_grid [N,P,3], gg_out [N,C,P].         */
+RECMV_API int recmv_gridsample3d_fwd(const void* input, const void* grid, void* output, int N, int C, int D,
+                           int H, int W, int64_t P, int dtype, int layout, recmv_stream_t stream);
+RECMV_API int recmv_gridsample3d_bwd(const void* input, const void* grid, const void* grad_out,
+                           void* grad_input, void* grad_grid, int N, int C, int D, int H, int W,
+                           int64_t P, int dtype, int layout, recmv_stream_t stream);
+RECMV_API int recmv_gridsample3d_bwd2(const void* gg_input, const void* gg_grid, const void* input,
+                            const void* grid, const void* grad_out, void* g_input, void* g_grid,
+                            void* gg_out, int N, int C, int D, int H, int W, int64_t P, int dtype,
+                            int layout, recmv_stream_t stream);
+/* [C,D,H,W] -> [D,H,W,C] copy (private cache of LBSkinner.ws) */
+RECMV_API int recmv_voxel_to_channels_last(const float* src, float* dst, int C, int D, int H, int W,
+                                 recmv_stream_t stream);
+
+/* ---- A12: MCGpu.mc_gpu --------------------------------------------------------------------
+ * replaces MCGpu/MCGpu.cpp:20-56 + CudaKernels.cu:316-521.  sdf [NX,NY,NZ] f32, z fastest.
+ * Deterministic: vertices and faces come out in the order a sequential sweep of the reference
+ * kernel (cell index ascending) would create them; faces int64 with the reference's reversed
+ * winding; vertices referenced on the far boundary planes get index -1 exactly as the reference.
+ * count: fills host V,F (blocks on the stream).  emit: must follow count on the same stream with
+ * the same sdf/iso/scratch; writes verts [V,3] = v*step+origin and faces [F,3].                 */
+RECMV_API int recmv_mc_scratch_bytes(int NX, int NY, int NZ, size_t* bytes /*host*/);
+RECMV_API int recmv_mc_count(const float* sdf, int NX, int NY, int NZ, float iso, void* scratch,
+                   int64_t* num_verts /*host*/, int64_t* num_faces /*host*/, recmv_stream_t stream);
+RECMV_API int recmv_mc_emit(const float* sdf, int NX, int NY, int NZ, float iso, void* scratch,
+                  const float step[3] /*host*/, const float origin[3] /*host*/, float* verts,
+                  int64_t* faces, recmv_stream_t stream);
+
+/* ---- A5 / A5': LBSkinner.forward and the inverse warp ----------------------------------------
+ * replaces model/Deformer.py:359-445 (+342-355, GridSamplerMine3dFunction at :421).
+ * ws_cl: skinning voxel channels-last [D,H,W,24] f32; A [F,24,4,4] row-major bone matrices
+ * (G*init_pose, computed on the host side); trans [F,3] (already + extra_trans);
+ * batch_inds [P] int64 or NULL (then frame = point / points_per_frame).
+ * fwd: out = (sum_j w_j(tp) A_j) [p;1] + trans;  tps may be NULL (= ps).
+ *      weights_out [P,24] optional (NULL to skip).
+ * inverse: x_c = M^-1 (x_obs - trans - t), [M|t] = sum_j w_j(x_obs) A_j ; valid=0 and x_c=0 when
+ *      |det M| < 1e-4 (FastMinv rule, Matrix3x3InvKernels.cu:40).                                */
+typedef struct {
+  const float* ws_cl;
+  int D, H, W;
+  float center[3];
+  float extend; /* nps = 2 (p - center) / extend   (Deformer.py:342-355) */
+} recmv_voxel_t;
+
+RECMV_API int recmv_lbs_fwd(const float* ps, const float* tps, const float* A, const float* trans,
+                  const int64_t* batch_inds, int64_t points_per_frame, int num_frames,
+                  const recmv_voxel_t* vox /*host*/, float* out, float* weights_out, int64_t P,
+                  recmv_stream_t stream);
+RECMV_API int recmv_lbs_inverse(const float* x_obs, const float* A, const float* trans,
+                      const int64_t* batch_inds, int64_t points_per_frame, int num_frames,
+                      const recmv_voxel_t* vox /*host*/, float* x_can, uint8_t* valid, int64_t P,
+                      recmv_stream_t stream);
+
+/* ---- A1+A2: Embedder + ImplicitNetwork.forward -------------------------------------------------
+ * replaces model/Embedder.py:43-50 + model/network.py:89-119 (+ utils/utils.py:40-46 weights).
+ * Network shape is the reference's getTmpSdf: PE(6) 39 -> 512 x3 -> 473 (+39 skip)/sqrt2 -> 512 x4
+ * -> 257, softplus(beta=100, threshold 20) on layers 0..7.
+ * pack: W_l [out_l, in_l] row-major fp32 EFFECTIVE weights (weight-norm already applied by the host
+ * shim), concatenated l = 0..8; b likewise.  `packed` (recmv_sdf_packed_bytes() bytes) holds the
+ * fp32 copy used by FP32_SIMT and the padded fp16 hi/lo K-major planes the TMA descriptors read.  */
+RECMV_API size_t recmv_sdf_packed_bytes(void);
+RECMV_API int recmv_sdf_pack_weights(const float* W_all, const float* b_all, void* packed,
+                           recmv_stream_t stream);
+/* x [P,3] canonical points; pe_w [12] host (annealing weights); out_sdf [P]; out_feat [P,256] or
+ * NULL.                                                                                           */
+RECMV_API int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float* pe_w /*host*/,
+                      float* out_sdf, float* out_feat, int64_t P, int mode, recmv_stream_t stream);
+
+/* ---- the fused render path (BASELINE north star) -------------------------------------------------
+ * One launch: ray r, sample k -> x_obs = cam_pos + t_k dir_r, t_k = t_near + (k+1/2)(t_far-t_near)/S
+ * -> inverse LBS (frame = frame_of_ray[r] or r / rays_per_frame) -> PE -> SDF MLP -> sdf [R,S].
+ * Per ray also: hit_idx[r] = first k with sdf_k <= 0 (-1 if none or if sample 0 is already inside),
+ * hit_t[r] = depth of the linear zero crossing between samples k-1 and k.
+ * out_xc [R,S,3] optional (NULL).  Samples whose inverse warp is singular get sdf = +1e10 (never hit).*/
+typedef struct {
+  float cam_pos[3];
+  float t_near, t_far;
+  int samples_per_ray;
+} recmv_raymarch_t;
+
+RECMV_API int recmv_render_sdf(const float* ray_dirs /*[R,3]*/, const recmv_raymarch_t* rm /*host*/,
+                     const float* A, const float* trans, const int32_t* frame_of_ray,
+                     int64_t rays_per_frame, int num_frames, const recmv_voxel_t* vox /*host*/,
+                     const void* packed, const float* pe_w /*host*/, float* out_sdf, float* out_xc,
+                     int32_t* hit_idx, float* hit_t, int64_t R, int mode, recmv_stream_t stream);
+/* second pass of the same launch sequence: per-ray first-hit scan over out_sdf (exposed for tests) */
+RECMV_API int recmv_ray_first_hit(const float* sdf /*[R,S]*/, const recmv_raymarch_t* rm /*host*/,
+                        int32_t* hit_idx, float* hit_t, int64_t R, recmv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECMV_B200_H_ */

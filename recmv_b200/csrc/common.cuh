@@ -1,0 +1,229 @@
+// Shared helpers for librecmv_b200.so (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/recmv_b200.h"
+
+namespace recmv {
+
+extern unsigned long long g_launch_count;  // defined in capi.cu
+
+inline int launch_status() {
+  ++g_launch_count;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear
+    return (int)e;
+  }
+  return RECMV_OK;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// grid for a grid-stride kernel: a whole number of waves over the SMs (148 on B200)
+inline int stride_grid(int64_t work, int threads, int ctas_per_sm) {
+  int64_t need = (work + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// Skinning voxel, channels-last [D,H,W,24] fp32, with the reference's normalisation
+// nps = 2 (p - c) / e   (model/Deformer.py:342-355)
+struct Voxel {
+  const float* ws;
+  int D, H, W;
+  float cx, cy, cz, ext;
+};
+
+inline Voxel to_voxel(const recmv_voxel_t* v) {
+  Voxel o;
+  o.ws = v->ws_cl; o.D = v->D; o.H = v->H; o.W = v->W;
+  o.cx = v->center[0]; o.cy = v->center[1]; o.cz = v->center[2]; o.ext = v->extend;
+  return o;
+}
+
+// ((g+1)*S-1)/2 exactly as GridSamplerMineKernel.cu:210-212 (the double literals there only
+// postpone one rounding across an exact halving, so the float result is identical), without
+// letting the compiler contract mul+sub into an FMA.
+__device__ __forceinline__ float unnormalize(float g, int size) {
+  float t = __fmul_rn(__fadd_rn(g, 1.f), (float)size);
+  return __fmul_rn(__fsub_rn(t, 1.f), 0.5f);
+}
+__device__ __forceinline__ double unnormalize(double g, int size) {
+  return ((g + 1.0) * (double)size - 1.0) / 2.0;
+}
+
+// clip_coordinates_set_grad (GridSamplerMineKernel.cu:42-59)
+template <typename T>
+__device__ __forceinline__ T clip_grad(T in, int size, T* mult) {
+  if (in <= (T)0) { *mult = (T)0; return (T)0; }
+  T mx = (T)(size - 1);
+  if (in >= mx) { *mult = (T)0; return mx; }
+  *mult = (T)1;
+  return in;
+}
+
+// Trilinear sample of the 24-channel channels-last skinning voxel at normalised point (gx,gy,gz).
+// Border-clamped coordinates can only address in-range corners or corners with zero weight, so the
+// reference's within_bounds tests reduce to clamping the +1 index.
+__device__ __forceinline__ void sample_skin24(const Voxel& v, float px, float py, float pz,
+                                              float w[24]) {
+  float gx = (px - v.cx) / v.ext * 2.f;
+  float gy = (py - v.cy) / v.ext * 2.f;
+  float gz = (pz - v.cz) / v.ext * 2.f;
+  float ix = fminf(fmaxf(unnormalize(gx, v.W), 0.f), (float)(v.W - 1));
+  float iy = fminf(fmaxf(unnormalize(gy, v.H), 0.f), (float)(v.H - 1));
+  float iz = fminf(fmaxf(unnormalize(gz, v.D), 0.f), (float)(v.D - 1));
+  if (!(ix == ix)) ix = 0.f;  // NaN guard (reference maps non-finite to -100 => zero output)
+  if (!(iy == iy)) iy = 0.f;
+  if (!(iz == iz)) iz = 0.f;
+  int x0 = (int)floorf(ix), y0 = (int)floorf(iy), z0 = (int)floorf(iz);
+  float fx = ix - (float)x0, fy = iy - (float)y0, fz = iz - (float)z0;
+  int x1 = min(x0 + 1, v.W - 1), y1 = min(y0 + 1, v.H - 1), z1 = min(z0 + 1, v.D - 1);
+  float wx[2] = {(float)(x0 + 1) - ix, fx};
+  float wy[2] = {(float)(y0 + 1) - iy, fy};
+  float wz[2] = {(float)(z0 + 1) - iz, fz};
+  int xs[2] = {x0, x1}, ys[2] = {y0, y1}, zs[2] = {z0, z1};
+#pragma unroll
+  for (int c = 0; c < 24; ++c) w[c] = 0.f;
+  // corner order tnw,tne,tsw,tse,bnw,bne,bsw,bse = (z,y,x) with x fastest, as the reference sums
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float cw = wx[dx] * wy[dy] * wz[dz];
+        const float4* p = reinterpret_cast<const float4*>(
+            v.ws + (((size_t)zs[dz] * v.H + ys[dy]) * v.W + xs[dx]) * 24);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          float4 t = __ldg(p + q);
+          w[4 * q + 0] = fmaf(t.x, cw, w[4 * q + 0]);
+          w[4 * q + 1] = fmaf(t.y, cw, w[4 * q + 1]);
+          w[4 * q + 2] = fmaf(t.z, cw, w[4 * q + 2]);
+          w[4 * q + 3] = fmaf(t.w, cw, w[4 * q + 3]);
+        }
+      }
+}
+
+// T[0..11] = rows 0..2 of sum_j w_j A_j  (A_j 4x4 row-major, 16 floats per bone)
+__device__ __forceinline__ void blend_bones(const float* __restrict__ Af, const float w[24],
+                                            float T[12]) {
+#pragma unroll
+  for (int e = 0; e < 12; ++e) T[e] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < 24; ++j) {
+    const float4* a = reinterpret_cast<const float4*>(Af + j * 16);
+    float4 r0 = __ldg(a), r1 = __ldg(a + 1), r2 = __ldg(a + 2);
+    float wj = w[j];
+    T[0] = fmaf(wj, r0.x, T[0]); T[1] = fmaf(wj, r0.y, T[1]); T[2] = fmaf(wj, r0.z, T[2]); T[3] = fmaf(wj, r0.w, T[3]);
+    T[4] = fmaf(wj, r1.x, T[4]); T[5] = fmaf(wj, r1.y, T[5]); T[6] = fmaf(wj, r1.z, T[6]); T[7] = fmaf(wj, r1.w, T[7]);
+    T[8] = fmaf(wj, r2.x, T[8]); T[9] = fmaf(wj, r2.y, T[9]); T[10] = fmaf(wj, r2.z, T[10]); T[11] = fmaf(wj, r2.w, T[11]);
+  }
+}
+
+// In-register 3x3 inverse with the FastMinv rule (Matrix3x3InvKernels.cu:29-60).
+// m row-major 9 floats; returns false (and zeros) when |det| < 1e-4.
+template <typename T>
+__device__ __forceinline__ bool inv3x3(const T m[9], T inv[9]) {
+  T c00 = m[4] * m[8] - m[5] * m[7];
+  T c01 = -m[3] * m[8] + m[5] * m[6];
+  T c02 = m[3] * m[7] - m[4] * m[6];
+  T c10 = -m[1] * m[8] + m[2] * m[7];
+  T c11 = m[0] * m[8] - m[2] * m[6];
+  T c12 = -m[0] * m[7] + m[1] * m[6];
+  T c20 = m[1] * m[5] - m[2] * m[4];
+  T c21 = -m[0] * m[5] + m[2] * m[3];
+  T c22 = m[0] * m[4] - m[1] * m[3];
+  T det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  if (fabs(det) < (T)0.0001) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) inv[i] = (T)0;
+    return false;
+  }
+  inv[0] = c00 / det; inv[1] = c10 / det; inv[2] = c20 / det;
+  inv[3] = c01 / det; inv[4] = c11 / det; inv[5] = c21 / det;
+  inv[6] = c02 / det; inv[7] = c12 / det; inv[8] = c22 / det;
+  return true;
+}
+
+// Inverse LBS of one observation-space point (SURVEY 8a row A5').
+__device__ __forceinline__ bool inverse_lbs_point(const Voxel& v, const float* __restrict__ Af,
+                                                  const float* __restrict__ tf, float ox, float oy,
+                                                  float oz, float& cx, float& cy, float& cz) {
+  float w[24], T[12];
+  sample_skin24(v, ox, oy, oz, w);
+  blend_bones(Af, w, T);
+  float M[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+  float Mi[9];
+  bool ok = inv3x3<float>(M, Mi);
+  float rx = ox - __ldg(tf + 0) - T[3];
+  float ry = oy - __ldg(tf + 1) - T[7];
+  float rz = oz - __ldg(tf + 2) - T[11];
+  cx = Mi[0] * rx + Mi[1] * ry + Mi[2] * rz;
+  cy = Mi[3] * rx + Mi[4] * ry + Mi[5] * rz;
+  cz = Mi[6] * rx + Mi[7] * ry + Mi[8] * rz;
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------
+// SDF network geometry (model/network.py:135-141 getTmpSdf)
+// ------------------------------------------------------------------------------------------
+constexpr int kNumLayers = 9;
+constexpr int kPE = 39;     // 3 + 3*2*6
+constexpr int kHidden = 512;
+constexpr int kSkipOut = 473;  // layer 3 out = 512 - 39
+constexpr int kOutDim = 257;   // 1 + 256
+__host__ __device__ constexpr int layer_in(int l) { return l == 0 ? kPE : kHidden; }
+__host__ __device__ constexpr int layer_out(int l) { return l == 3 ? kSkipOut : (l == 8 ? kOutDim : kHidden); }
+
+// Packed weight blob layout (see sdf_pack.cu)
+struct PackedLayout {
+  size_t w32_off[kNumLayers];   // fp32 [out, in] row-major
+  size_t b32_off[kNumLayers];   // fp32 [out]
+  size_t f16_off[kNumLayers];   // fp16 planes: hi [Npad, Kpad] then lo [Npad, Kpad], K-major
+  size_t bpad_off[kNumLayers];  // fp32 [Npad] bias padded with zeros
+  int Npad[kNumLayers], Kpad[kNumLayers];
+  size_t total;
+};
+PackedLayout packed_layout();
+
+// positional encoding of one point: pe[0..2] = x, then per band k: w*sin(2^k x) (3), w*cos(2^k x) (3)
+// (model/Embedder.py:33-37 order), accurate sincosf (fast intrinsics lose >1e-4 at 32x).
+__device__ __forceinline__ void positional_encode(float x, float y, float z,
+                                                  const float* __restrict__ pw /*12*/, float pe[39]) {
+  pe[0] = x; pe[1] = y; pe[2] = z;
+  float f = 1.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float sx, cxv, sy, cyv, sz, czv;
+    sincosf(x * f, &sx, &cxv);
+    sincosf(y * f, &sy, &cyv);
+    sincosf(z * f, &sz, &czv);
+    float ws = pw[2 * k], wc = pw[2 * k + 1];
+    pe[3 + 6 * k + 0] = ws * sx; pe[3 + 6 * k + 1] = ws * sy; pe[3 + 6 * k + 2] = ws * sz;
+    pe[3 + 6 * k + 3] = wc * cxv; pe[3 + 6 * k + 4] = wc * cyv; pe[3 + 6 * k + 5] = wc * czv;
+    f *= 2.f;
+  }
+}
+
+// softplus(beta=100, threshold=20) as torch: x*beta > 20 ? x : log1p(exp(beta x))/beta
+__device__ __forceinline__ float softplus100(float x) {
+  float bx = 100.f * x;
+  return bx > 20.f ? x : log1pf(expf(bx)) * 0.01f;
+}
+
+}  // namespace recmv

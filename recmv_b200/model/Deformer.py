@@ -1,0 +1,265 @@
+"""CompositeDeformer / MLPTranslator / LBSkinner with the reference's API (model/Deformer.py:22-34,
+141-206, 216-531).  Buffer names of LBSkinner (b_min, b_max, ws, extra_trans, bbox_extend,
+bbox_center, Js, init_pose) and parameter names of MLPTranslator (lin{0..4}.{weight,bias}) are kept so
+reference checkpoints load.
+
+LBSkinner.forward:
+  * bone matrices A = G . init_pose are built on the host side in torch (24 joints, tiny);
+  * no autograd needed -> ONE fused launch (voxel sample + blend + apply, recmv_lbs_fwd) over the
+    channels-last cache of `ws` (rebuilt when `ws` changes, e.g. load_state_dict);
+  * autograd needed -> the CUDA GridSamplerMine3dFunction (twice differentiable) + batched blend,
+    without the reference's per-frame python loop and its `.item()` sync (Deformer.py:438-444).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .Embedder import get_embedder, ratio_to_weights
+
+
+def quat2mat(quat):
+    """utils/utils.py:21-38."""
+    q = quat / quat.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    B = quat.size(0)
+    w2, x2, y2, z2 = w.pow(2), x.pow(2), y.pow(2), z.pow(2)
+    wx, wy, wz = w * x, w * y, w * z
+    xy, xz, yz = x * y, x * z, y * z
+    return torch.stack([w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
+                        2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
+                        2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2], dim=1).view(B, 3, 3)
+
+
+def batch_rodrigues(theta):
+    """smpl_pytorch.util.batch_rodrigues (un-vendored dependency of the reference; standard HMR
+    form -- parity unpinned)."""
+    l1norm = torch.norm(theta + 1e-8, p=2, dim=1)
+    angle = torch.unsqueeze(l1norm, -1)
+    normalized = torch.div(theta, angle)
+    angle = angle * 0.5
+    quat = torch.cat([torch.cos(angle), torch.sin(angle) * normalized], dim=1)
+    return quat2mat(quat)
+
+
+class CompositeDeformer(nn.Module):
+    def __init__(self, deformers):
+        super().__init__()
+        self.N = len(deformers)
+        self.defs = nn.ModuleList(deformers)
+
+    def forward(self, ps, conds, batch_inds=None, **kwargs):
+        assert (self.N == len(conds))
+        out = ps
+        for cond, deformer in zip(conds, self.defs):
+            out = deformer(out, cond, batch_inds, **kwargs)
+        return out
+
+
+class MLPTranslator(nn.Module):
+    """167 -> 512 x4 ReLU -> 3 offset MLP (model/Deformer.py:141-206)."""
+
+    def __init__(self, feature_vector_size, multires, weight_norm=False):
+        super().__init__()
+        dims = [3 + feature_vector_size, 512, 512, 512, 512, 3]
+        self.feature_vector_size = feature_vector_size
+        self.embed_fn = None
+        self.multires = multires
+        if multires > 0:
+            embed_fn, input_ch = get_embedder(multires)
+            self.embed_fn = embed_fn
+            dims[0] = input_ch + feature_vector_size
+        self.num_layers = len(dims)
+        for l in range(0, self.num_layers - 1):
+            lin = nn.Linear(dims[l], dims[l + 1])
+            if l == self.num_layers - 2:
+                torch.nn.init.normal_(lin.weight, mean=0., std=0.001)
+                torch.nn.init.constant_(lin.bias, 0.)
+            setattr(self, "lin" + str(l), lin)
+        self.relu = nn.ReLU()
+        self.offset = {}
+
+    def forward(self, ps, conds, batch_inds=None, **kwargs):
+        ratio = kwargs['ratio']['deformerRatio']
+        offset_type = kwargs['offset_type']
+        if self.embed_fn is not None:
+            ps = self.embed_fn(ps, ratio_to_weights(self.multires, ratio))
+        if batch_inds is not None:
+            x = torch.cat([ps, conds[batch_inds]], dim=1)
+        else:
+            x = torch.cat([ps, conds.view(-1, 1, self.feature_vector_size).expand(
+                -1, ps.shape[1], self.feature_vector_size)], dim=-1).view(-1, ps.shape[-1] + self.feature_vector_size)
+        for l in range(0, self.num_layers - 1):
+            x = getattr(self, "lin" + str(l))(x)
+            if l < self.num_layers - 2:
+                x = self.relu(x)
+        if batch_inds is not None:
+            self.offset[offset_type] = x
+            return ps[..., :3] + x
+        self.offset[offset_type] = x.view(ps.shape[0], ps.shape[1], 3)
+        return ps[..., :3] + x.view(ps.shape[0], ps.shape[1], 3)
+
+
+def getTranslatorNet(device, conf):
+    return MLPTranslator(conf.get_int('condlen'), multires=conf.get_int('multires')).to(device)
+
+
+class LBSkinner(nn.Module):
+    def __init__(self, ws, bmins, bmaxs, Js, parents, init_pose=None, align_corners=False,
+                 extra_trans=None, bbox_extend=None, bbox_center=None):
+        super().__init__()
+
+        def as_buf(v):
+            if type(v) is list:
+                return torch.tensor(v, dtype=torch.float).view(1, 3)
+            if type(v) is np.ndarray:
+                return torch.from_numpy(v.astype(np.float32)).view(1, 3)
+            return v.view(1, 3)
+        self.register_buffer('b_min', as_buf(bmins))
+        self.register_buffer('b_max', as_buf(bmaxs))
+        if type(ws) is np.ndarray:
+            ws = torch.from_numpy(ws.astype(np.float32))
+        self.register_buffer('ws', ws.to(torch.float))
+        if extra_trans is None:
+            extra_trans = torch.full([1, 3], 0.).float()
+        self.register_buffer('extra_trans', extra_trans.to(torch.float))
+        self.register_buffer('bbox_extend', torch.as_tensor(bbox_extend).to(torch.float))
+        self.register_buffer('bbox_center', torch.as_tensor(bbox_center).to(torch.float))
+        self.align_corners = align_corners
+        assert (align_corners == False)
+        self.register_buffer('Js', Js.view(24, 3))
+        self.parents = parents
+        if init_pose is None:
+            self.register_buffer('init_pose', None)
+        else:
+            if type(init_pose) == np.ndarray:
+                init_pose = torch.from_numpy(init_pose.astype(np.float32))
+            if init_pose.numel() == 24 * 3:
+                self.init_pose_inverse(batch_rodrigues(init_pose.view(-1, 3)).view(24, 3, 3), self.Js)
+            else:
+                self.register_buffer('init_pose', init_pose.view(24, 4, 4))
+        self._ws_cl = None
+        self._ws_key = None
+        self.last_path = None
+
+    def bbox_size(self):
+        margin = torch.tensor([0.15, 0.15, 0.20]).to(self.b_min)
+        return self.b_min - margin, self.b_max + margin
+
+    def init_pose_inverse(self, init_pose, Js):
+        """model/Deformer.py:280-303."""
+        resultsR = [init_pose[0]]
+        resultsT = [Js[0]]
+        for i in range(1, self.parents.shape[0]):
+            j_here = Js[i] - Js[self.parents[i]]
+            resultsR.append(resultsR[self.parents[i]].matmul(init_pose[i]))
+            resultsT.append(resultsR[self.parents[i]].matmul(j_here.view(-1, 1)).view(-1) + resultsT[self.parents[i]])
+        invs = []
+        for R, T in zip(resultsR, resultsT):
+            inv = torch.zeros(4, 4)
+            inv[3, 3] = 1.
+            inv[:3, :3] = R.transpose(0, 1)
+            inv[:3, 3] = (-T.view(1, -1).matmul(R)).view(-1)
+            invs.append(inv)
+        self.register_buffer('init_pose', torch.stack(invs, dim=0))
+
+    # -- skeleton ---------------------------------------------------------------------------------
+    def _chain(self, poses):
+        batch_size = poses.shape[0]
+        R = batch_rodrigues(poses.view(-1, 3)).view(batch_size, 24, 3, 3)
+        Js = self.Js.view(1, 24, 3, 1).expand(batch_size, 24, 3, 1)
+
+        def make_A(Rm, t):
+            R_homo = F.pad(Rm, [0, 0, 0, 1, 0, 0])
+            t_homo = torch.cat([t, torch.ones(Rm.shape[0], 1, 1).to(Rm.device)], dim=1)
+            return torch.cat([R_homo, t_homo], 2)
+        results = [make_A(R[:, 0], Js[:, 0])]
+        parent = self.parents
+        for i in range(1, parent.shape[0]):
+            results.append(torch.matmul(results[int(parent[i])], make_A(R[:, i], Js[:, i] - Js[:, int(parent[i])])))
+        return torch.stack(results, dim=1), Js
+
+    def bone_matrices(self, poses):
+        """A [N,24,4,4] = G . init_pose (Deformer.py:372-405)."""
+        results, Js = self._chain(poses)
+        batch_size = poses.shape[0]
+        if self.init_pose is None:
+            Js_w0 = torch.cat([Js, torch.zeros(batch_size, 24, 1, 1).to(poses.device)], dim=2)
+            init_bone = F.pad(torch.matmul(results, Js_w0), [3, 0, 0, 0, 0, 0, 0, 0])
+            return results - init_bone
+        return torch.matmul(results, self.init_pose.view(1, 24, 4, 4).expand(batch_size, 24, 4, 4))
+
+    def posedSkeleton(self, conds):
+        poses, trans = conds
+        assert (poses.shape[0] == trans.shape[0])
+        results, _ = self._chain(poses)
+        return results[:, :, :3, 3]
+
+    def inv_transform_v(self, v, scale_grid, transl):
+        v = v - transl[None, None]
+        v = v / scale_grid
+        v = v * 2
+        return v
+
+    def ws_channels_last(self):
+        key = (self.ws.data_ptr(), self.ws._version)
+        if self._ws_cl is None or key != self._ws_key:
+            if self.ws.shape[1] != 24:
+                raise RuntimeError("LBSkinner expects a 24-channel skinning voxel")
+            self._ws_cl = ops.voxel_to_channels_last(self.ws.contiguous())
+            self._ws_key = key
+        return self._ws_cl
+
+    def forward(self, ps, conds, batch_inds=None, **kwargs):
+        if type(ps) == list:
+            tps, ps = ps
+        else:
+            tps = ps
+        poses, trans = conds
+        trans = trans + self.extra_trans
+        batch_size = poses.shape[0]
+        assert (batch_size == trans.shape[0])
+        A = self.bone_matrices(poses)
+        needs_graph = torch.is_grad_enabled() and any(
+            t.requires_grad for t in (ps, tps, poses, trans))
+        if not ps.is_cuda:
+            raise RuntimeError("recmv_b200.LBSkinner runs on CUDA tensors only (no CPU path)")
+        center = self.bbox_center.view(-1)[:3].tolist()
+        extend = float(self.bbox_extend.view(-1)[0])
+        if not needs_graph:
+            self.last_path = "fused"
+            if batch_inds is None:
+                bsz, pnum, _ = ps.shape
+                assert (batch_size == bsz)
+                out = ops.lbs_forward(ps.reshape(-1, 3), A, trans, self.ws_channels_last(), center, extend,
+                                      None, pnum, None if tps is ps else tps.reshape(-1, 3))
+                return out.view(bsz, pnum, 3)
+            out = ops.lbs_forward(ps.reshape(-1, 3), A, trans, self.ws_channels_last(), center, extend,
+                                  batch_inds, 0, None if tps is ps else tps.reshape(-1, 3))
+            return out
+        self.last_path = "autograd-composite"
+        nps = self.inv_transform_v(tps, self.bbox_extend, self.bbox_center).view(-1, 3)
+        ps_ws = ops.GridSamplerMine3dFunction.apply(self.ws, nps.reshape(1, 1, 1, -1, 3)).view(-1, nps.shape[0]).transpose(0, 1)
+        if batch_inds is None:
+            bsz, pnum, _ = ps.shape
+            T = torch.matmul(ps_ws.view(bsz, pnum, 24), A.view(batch_size, 24, 16)).view(bsz, pnum, 4, 4)
+            vh = torch.cat([ps, torch.ones(bsz, pnum, 1, device=ps.device)], dim=2)
+            return torch.matmul(T, vh.unsqueeze(-1))[:, :, :3, 0] + trans.view(-1, 1, 3)
+        ps = ps.reshape(-1, 3)
+        T = torch.einsum('pj,pjk->pk', ps_ws, A.view(batch_size, 24, 16)[batch_inds]).view(-1, 4, 4)
+        vh = F.pad(ps, (0, 1), mode='constant', value=1).unsqueeze(-1)
+        return torch.matmul(T, vh)[:, :3, 0] + trans[batch_inds]
+
+    def inverse(self, x_obs, conds, batch_inds=None):
+        """North-star inverse warp (observation -> canonical) with the FastMinv singularity rule."""
+        poses, trans = conds
+        trans = trans + self.extra_trans
+        A = self.bone_matrices(poses)
+        center = self.bbox_center.view(-1)[:3].tolist()
+        extend = float(self.bbox_extend.view(-1)[0])
+        shp = x_obs.shape
+        ppf = 0 if batch_inds is not None else (x_obs.shape[1] if x_obs.dim() == 3 else x_obs.shape[0])
+        xc, ok = ops.lbs_inverse(x_obs.reshape(-1, 3), A, trans, self.ws_channels_last(), center, extend,
+                                 batch_inds, ppf)
+        return xc.view(shp), ok

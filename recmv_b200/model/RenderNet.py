@@ -1,0 +1,57 @@
+"""IDR colour MLP with the reference's API (model/RenderNet.py:10-103): cat[p, PE4(v), n, feat] = 289
+-> 512 x4 ReLU -> 3 -> tanh, weight-normed.  Evaluated once per RAY (not per sample); runs as a torch
+graph over cuBLAS in this round (SURVEY 8a row A8, 1.9 MFLOP/ray = 0.7 % of the per-ray work)."""
+import torch
+import torch.nn as nn
+
+from .Embedder import get_embedder, ratio_to_weights
+
+
+class RenderingNetwork_view_norm(nn.Module):
+    def __init__(self, feature_vector_size, mode, d_in, d_out, dims, weight_norm=True, multires_n=0,
+                 multires_v=0):
+        super().__init__()
+        self.mode = mode
+        dims = [d_in + feature_vector_size] + dims + [d_out]
+        self.embedv_fn = None
+        self.multires_v = multires_v
+        if multires_v > 0:
+            self.embedv_fn, input_ch = get_embedder(multires_v)
+            dims[0] += (input_ch - 3)
+        self.embedn_fn = None
+        self.multires_n = multires_n
+        if multires_n > 0:
+            self.embedn_fn, input_ch = get_embedder(multires_n)
+            dims[0] += (input_ch - 3)
+        self.num_layers = len(dims)
+        for l in range(0, self.num_layers - 1):
+            lin = nn.Linear(dims[l], dims[l + 1])
+            if weight_norm:
+                lin = nn.utils.weight_norm(lin)
+            setattr(self, "lin" + str(l), lin)
+        self.relu = nn.ReLU()
+        self.tanh = nn.Tanh()
+
+    def forward(self, points, normals, view_dirs, feature_vectors, ratio):
+        ratio = ratio['renderRatio']
+        if self.embedv_fn is not None:
+            view_dirs = self.embedv_fn(view_dirs, ratio_to_weights(self.multires_v, ratio))
+        if self.embedn_fn is not None:
+            normals = self.embedn_fn(normals, ratio_to_weights(self.multires_n, ratio))
+        if self.mode == 'idr':
+            x = torch.cat([points, view_dirs, normals, feature_vectors], dim=-1)
+        elif self.mode == 'no_view_dir':
+            x = torch.cat([points, normals, feature_vectors], dim=-1)
+        elif self.mode == 'no_normal':
+            x = torch.cat([points, view_dirs, feature_vectors], dim=-1)
+        for l in range(0, self.num_layers - 1):
+            x = getattr(self, "lin" + str(l))(x)
+            if l < self.num_layers - 2:
+                x = self.relu(x)
+        return self.tanh(x)
+
+
+def getRenderNet(device, conf):
+    return RenderingNetwork_view_norm(conf.get_int('condlen'), d_in=9, d_out=3, dims=[512, 512, 512, 512],
+                                      mode='idr', weight_norm=True, multires_v=conf.get_int('multires_v'),
+                                      multires_n=conf.get_int('multires_n')).to(device)

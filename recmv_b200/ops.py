@@ -1,0 +1,389 @@
+"""Torch-facing wrappers over the C ABI: allocate outputs, pass raw pointers + the current stream,
+raise on non-zero status, wire autograd.  PyTorch is plumbing here (device memory, streams,
+autograd graph); all arithmetic happens in librecmv_b200.so.
+"""
+import ctypes
+from ctypes import byref, c_float, c_int64, c_size_t
+
+import torch
+
+from . import _lib
+from ._lib import (F32, F64, LAYOUT_NCDHW, LAYOUT_NDHWC, MLP_FP32_SIMT, MLP_TC_F16X1, MLP_TC_F16X3,
+                   RayMarch, Voxel, check)
+
+DEFAULT_MLP_MODE = MLP_TC_F16X3
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _check_input(t, name):
+    # reference: CHECK_INPUT (FastMinv/M3x3Inv.cpp:4-6, MCGpu/MCGpu.cpp:3-5)
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def _dtype_code(t, name):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise RuntimeError(f"{name} must be a float/double tensor")
+
+
+# --------------------------------------------------------------------------------------------------
+# FastMinv
+# --------------------------------------------------------------------------------------------------
+def minv3x3(ms):
+    """FastMinv.Fast3x3Minv(ms) -> [invs, checks]  (FastMinv/M3x3Inv.cpp:12-37)."""
+    _check_input(ms, "ms")
+    code = _dtype_code(ms, "ms")
+    n = ms.size(0)
+    invs = torch.empty((n, 3, 3), dtype=ms.dtype, device=ms.device)
+    ok = torch.empty((n,), dtype=torch.uint8, device=ms.device)
+    with torch.cuda.device(ms.device):
+        check(_lib.load().recmv_minv3x3_fwd(_ptr(ms), _ptr(invs), _ptr(ok), n, code, _stream(ms)),
+              "recmv_minv3x3_fwd")
+    return [invs, ok.view(torch.bool)]
+
+
+def minv3x3_backward(grads, invs):
+    """FastMinv.Fast3x3Minv_backward(grads, invs) -> outs  (FastMinv/M3x3Inv.cpp:39-59)."""
+    _check_input(grads, "grads")
+    _check_input(invs, "invs")
+    if grads.dtype != invs.dtype:
+        raise RuntimeError("invs must have same type with grads")
+    code = _dtype_code(invs, "invs")
+    n = invs.size(0)
+    outs = torch.empty((n, 3, 3), dtype=invs.dtype, device=invs.device)
+    with torch.cuda.device(invs.device):
+        check(_lib.load().recmv_minv3x3_bwd(_ptr(grads), _ptr(invs), _ptr(outs), n, code,
+                                            _stream(invs)), "recmv_minv3x3_bwd")
+    return outs
+
+
+class FastDiff3x3MinvFunction(torch.autograd.Function):
+    """utils/utils.py:8-18."""
+
+    @staticmethod
+    def forward(ctx, input):
+        invs, chk = minv3x3(input.contiguous())
+        ctx.save_for_backward(invs, chk)
+        ctx.mark_non_differentiable(chk)
+        return invs, chk
+
+    @staticmethod
+    def backward(ctx, grad_input, grad_check):
+        invs, _ = ctx.saved_tensors
+        return minv3x3_backward(grad_input.contiguous(), invs), None
+
+
+# --------------------------------------------------------------------------------------------------
+# GridSamplerMine
+# --------------------------------------------------------------------------------------------------
+def _gs_dims(inp, grid, layout):
+    if inp.dim() != 5 or grid.dim() != 5:
+        raise RuntimeError("grid_sampler(): expected 5D input and grid")
+    if inp.size(0) != grid.size(0) or grid.size(-1) != 3:
+        raise RuntimeError("grid_sampler(): inconsistent input / grid sizes")
+    if inp.dtype != grid.dtype:
+        raise RuntimeError("grid_sampler(): expected input and grid to have same dtype")
+    if layout == LAYOUT_NCDHW:
+        N, C, D, H, W = inp.shape
+    else:
+        N, D, H, W, C = inp.shape
+    P = grid.size(1) * grid.size(2) * grid.size(3)
+    return N, C, D, H, W, P
+
+
+def grid_sample3d_forward(inp, grid, layout=LAYOUT_NCDHW):
+    """GridSamplerMine.forward(input, grid, 0, 1)  (MCAcc/cuda/GridSamplerMine.cpp:75-81)."""
+    _check_input(inp, "input")
+    _check_input(grid, "grid")
+    code = _dtype_code(inp, "input")
+    N, C, D, H, W, P = _gs_dims(inp, grid, layout)
+    out = torch.empty((N, C, grid.size(1), grid.size(2), grid.size(3)), dtype=inp.dtype,
+                      device=inp.device)
+    with torch.cuda.device(inp.device):
+        check(_lib.load().recmv_gridsample3d_fwd(_ptr(inp), _ptr(grid), _ptr(out), N, C, D, H, W, P,
+                                                 code, layout, _stream(inp)),
+              "recmv_gridsample3d_fwd")
+    return out
+
+
+def grid_sample3d_backward(inp, grid, grad_out, layout=LAYOUT_NCDHW, need_grad_input=True):
+    """GridSamplerMine.backward(input, grid, grad_output, 0, 1) -> (grad_input, grad_grid)."""
+    _check_input(inp, "input")
+    _check_input(grid, "grid")
+    grad_out = grad_out.contiguous()
+    code = _dtype_code(inp, "input")
+    N, C, D, H, W, P = _gs_dims(inp, grid, layout)
+    gi = torch.zeros_like(inp) if need_grad_input else None
+    gg = torch.empty_like(grid)
+    with torch.cuda.device(inp.device):
+        check(_lib.load().recmv_gridsample3d_bwd(_ptr(inp), _ptr(grid), _ptr(grad_out), _ptr(gi),
+                                                 _ptr(gg), N, C, D, H, W, P, code, layout,
+                                                 _stream(inp)), "recmv_gridsample3d_bwd")
+    return gi, gg
+
+
+def grid_sample3d_dbackward(gg_input, gg_grid, inp, grid, grad_out, layout=LAYOUT_NCDHW,
+                            need_grad_input=True):
+    """GridSamplerMine.dbackward(ggI, ggG, input, grid, grad_output, 0, 1) -> (gI, gG, ggO)."""
+    _check_input(inp, "input")
+    _check_input(grid, "grid")
+    grad_out = grad_out.contiguous()
+    gg_grid = gg_grid.contiguous()
+    if gg_input is not None:
+        gg_input = gg_input.contiguous()
+    code = _dtype_code(inp, "input")
+    N, C, D, H, W, P = _gs_dims(inp, grid, layout)
+    gi = torch.zeros_like(inp) if need_grad_input else None
+    gg = torch.empty_like(grid)
+    ggo = torch.empty_like(grad_out)
+    with torch.cuda.device(inp.device):
+        check(_lib.load().recmv_gridsample3d_bwd2(_ptr(gg_input), _ptr(gg_grid), _ptr(inp), _ptr(grid),
+                                                  _ptr(grad_out), _ptr(gi), _ptr(gg), _ptr(ggo), N, C,
+                                                  D, H, W, P, code, layout, _stream(inp)),
+              "recmv_gridsample3d_bwd2")
+    return gi, gg, ggo
+
+
+class GridSamplerMine3dFunction(torch.autograd.Function):
+    """MCAcc/grid_sampler_mine.py:8-46 -- twice differentiable trilinear/border sampler."""
+
+    @staticmethod
+    def forward(ctx, input, grid, mode="bilinear", padding_mode="border", align_corners=False):
+        if align_corners:
+            raise NotImplementedError
+        input = input.contiguous()
+        grid = grid.contiguous()
+        ctx.save_for_backward(input, grid)
+        return grid_sample3d_forward(input, grid)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, grid = ctx.saved_tensors
+        o0, o1 = GridSamplerMine3dBackwardFunction.apply(input, grid, grad_output)
+        return o0, o1, None, None, None
+
+
+class GridSamplerMine3dBackwardFunction(torch.autograd.Function):
+    """MCAcc/grid_sampler_mine.py:48-65.  grad_input is only materialised when the voxel itself
+    requires grad (the reference always fills a full zero volume, GridSamplerMineKernel.cu:955)."""
+
+    @staticmethod
+    def forward(ctx, input, grid, grad_output):
+        ctx.save_for_backward(input, grid, grad_output)
+        ctx.need_gi = bool(input.requires_grad)
+        gi, gg = grid_sample3d_backward(input, grid, grad_output, need_grad_input=ctx.need_gi)
+        if gi is None:
+            gi = input.new_zeros(())  # placeholder, never consumed (input does not require grad)
+            ctx.mark_non_differentiable(gi)
+        return gi, gg
+
+    @staticmethod
+    def backward(ctx, grad_output_input, grad_output_grid):
+        input, grid, grad_output = ctx.saved_tensors
+        ggi = grad_output_input if ctx.need_gi else None
+        if grad_output_grid is None:
+            grad_output_grid = torch.zeros_like(grid)
+        o0, o1, o2 = grid_sample3d_dbackward(ggi, grad_output_grid, input, grid, grad_output,
+                                             need_grad_input=ctx.need_gi)
+        return o0, o1, o2
+
+
+def voxel_to_channels_last(ws):
+    """[1,C,D,H,W] fp32 -> [D,H,W,C] (private, coalesced copy of LBSkinner.ws)."""
+    _check_input(ws, "ws")
+    _, C, D, H, W = ws.shape
+    out = torch.empty((D, H, W, C), dtype=torch.float32, device=ws.device)
+    with torch.cuda.device(ws.device):
+        check(_lib.load().recmv_voxel_to_channels_last(_ptr(ws), _ptr(out), C, D, H, W, _stream(ws)),
+              "recmv_voxel_to_channels_last")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# MCGpu
+# --------------------------------------------------------------------------------------------------
+_mc_scratch = {}
+
+
+def mc_gpu(sdfs, xstep=1.0, ystep=1.0, zstep=1.0, xmin=0.0, ymin=0.0, zmin=0.0, fTargetValue=0.0):
+    """MCGpu.mc_gpu(sdfs, steps, mins, iso) -> [verts [V,3] f32, faces [F,3] i64]
+    (MCGpu/MCGpu.cpp:20-56).  Wrong dtype returns [] exactly like the reference (:41-42)."""
+    _check_input(sdfs, "sdfs")
+    if sdfs.dtype != torch.float32:
+        return []
+    if sdfs.dim() != 3 or min(sdfs.shape) <= 0:
+        return []
+    NX, NY, NZ = sdfs.shape
+    lib = _lib.load()
+    nbytes = c_size_t(0)
+    check(lib.recmv_mc_scratch_bytes(NX, NY, NZ, byref(nbytes)), "recmv_mc_scratch_bytes")
+    key = (sdfs.device.index, )
+    scratch = _mc_scratch.get(key)
+    if scratch is None or scratch.numel() < nbytes.value:  # grow-only, like the MCGpu singleton
+        scratch = torch.empty((nbytes.value,), dtype=torch.uint8, device=sdfs.device)
+        _mc_scratch[key] = scratch
+    V, F = c_int64(0), c_int64(0)
+    with torch.cuda.device(sdfs.device):
+        st = _stream(sdfs)
+        check(lib.recmv_mc_count(_ptr(sdfs), NX, NY, NZ, float(fTargetValue), _ptr(scratch), byref(V),
+                                 byref(F), st), "recmv_mc_count")
+        verts = torch.empty((V.value, 3), dtype=torch.float32, device=sdfs.device)
+        faces = torch.empty((F.value, 3), dtype=torch.int64, device=sdfs.device)
+        if V.value > 0:
+            step = (c_float * 3)(xstep, ystep, zstep)
+            org = (c_float * 3)(xmin, ymin, zmin)
+            check(lib.recmv_mc_emit(_ptr(sdfs), NX, NY, NZ, float(fTargetValue), _ptr(scratch), step,
+                                    org, _ptr(verts), _ptr(faces) if F.value > 0 else None, st),
+                  "recmv_mc_emit")
+    return [verts, faces]
+
+
+# --------------------------------------------------------------------------------------------------
+# LBS
+# --------------------------------------------------------------------------------------------------
+def make_voxel(ws_cl, center, extend):
+    v = Voxel()
+    v.ws_cl = ws_cl.data_ptr()
+    v.D, v.H, v.W = int(ws_cl.shape[0]), int(ws_cl.shape[1]), int(ws_cl.shape[2])
+    c = [float(x) for x in center]
+    v.center = (c_float * 3)(*c)
+    v.extend = float(extend)
+    return v
+
+
+def lbs_forward(ps, A, trans, ws_cl, center, extend, batch_inds=None, points_per_frame=0, tps=None,
+                want_weights=False):
+    ps = ps.contiguous().float()
+    A = A.contiguous().float()
+    trans = trans.contiguous().float()
+    P = ps.numel() // 3
+    out = torch.empty_like(ps)
+    wout = torch.empty((P, 24), dtype=torch.float32, device=ps.device) if want_weights else None
+    if tps is not None:
+        tps = tps.contiguous().float()
+    if batch_inds is not None:
+        batch_inds = batch_inds.contiguous().long()
+    vox = make_voxel(ws_cl, center, extend)
+    with torch.cuda.device(ps.device):
+        check(_lib.load().recmv_lbs_fwd(_ptr(ps), _ptr(tps), _ptr(A), _ptr(trans), _ptr(batch_inds),
+                                        int(points_per_frame), int(A.shape[0]), byref(vox), _ptr(out),
+                                        _ptr(wout), P, _stream(ps)), "recmv_lbs_fwd")
+    return (out, wout) if want_weights else out
+
+
+def lbs_inverse(x_obs, A, trans, ws_cl, center, extend, batch_inds=None, points_per_frame=0):
+    x_obs = x_obs.contiguous().float()
+    A = A.contiguous().float()
+    trans = trans.contiguous().float()
+    P = x_obs.numel() // 3
+    xc = torch.empty_like(x_obs)
+    valid = torch.empty((P,), dtype=torch.uint8, device=x_obs.device)
+    if batch_inds is not None:
+        batch_inds = batch_inds.contiguous().long()
+    vox = make_voxel(ws_cl, center, extend)
+    with torch.cuda.device(x_obs.device):
+        check(_lib.load().recmv_lbs_inverse(_ptr(x_obs), _ptr(A), _ptr(trans), _ptr(batch_inds),
+                                            int(points_per_frame), int(A.shape[0]), byref(vox),
+                                            _ptr(xc), _ptr(valid), P, _stream(x_obs)),
+              "recmv_lbs_inverse")
+    return xc, valid.view(torch.bool)
+
+
+# --------------------------------------------------------------------------------------------------
+# SDF MLP
+# --------------------------------------------------------------------------------------------------
+SDF_LAYER_SHAPES = [(512, 39), (512, 512), (512, 512), (473, 512), (512, 512), (512, 512), (512, 512),
+                    (512, 512), (257, 512)]
+
+
+def sdf_pack_weights(Ws, bs):
+    """Ws[l] [out,in] effective fp32 weights (weight-norm applied), bs[l] [out] -> packed device blob."""
+    dev = Ws[0].device
+    for (o, i), W, b in zip(SDF_LAYER_SHAPES, Ws, bs):
+        if tuple(W.shape) != (o, i) or tuple(b.shape) != (o,):
+            raise RuntimeError(f"unexpected SDF layer shape {tuple(W.shape)} (want {(o, i)})")
+    W_all = torch.cat([W.detach().reshape(-1).float() for W in Ws]).contiguous()
+    b_all = torch.cat([b.detach().reshape(-1).float() for b in bs]).contiguous()
+    lib = _lib.load()
+    nbytes = lib.recmv_sdf_packed_bytes()
+    # 1 KiB alignment for the TMA-visible planes
+    raw = torch.empty((nbytes + 1024,), dtype=torch.uint8, device=dev)
+    off = (-raw.data_ptr()) % 1024
+    packed = raw[off:off + nbytes]
+    with torch.cuda.device(dev):
+        check(lib.recmv_sdf_pack_weights(_ptr(W_all), _ptr(b_all), _ptr(packed), _stream(W_all)),
+              "recmv_sdf_pack_weights")
+    packed._keepalive = raw
+    return packed
+
+
+def _pe_array(pe_w):
+    pe_w = [1.0] * 12 if pe_w is None else [float(w) for w in pe_w]
+    if len(pe_w) != 12:
+        raise RuntimeError("pe_w must hold 12 annealing weights")
+    return (c_float * 12)(*pe_w)
+
+
+def sdf_mlp_forward(x, packed, pe_w=None, mode=None, want_feat=True):
+    """ImplicitNetwork.forward on canonical points x [P,3] -> (sdf [P,1], feat [P,256] or None)."""
+    mode = DEFAULT_MLP_MODE if mode is None else mode
+    x = x.contiguous().float()
+    _check_input(x, "x")
+    P = x.shape[0]
+    sdf = torch.empty((P, 1), dtype=torch.float32, device=x.device)
+    feat = torch.empty((P, 256), dtype=torch.float32, device=x.device) if want_feat else None
+    with torch.cuda.device(x.device):
+        check(_lib.load().recmv_sdf_mlp_fwd(_ptr(x), _ptr(packed), _pe_array(pe_w), _ptr(sdf),
+                                            _ptr(feat), P, mode, _stream(x)), "recmv_sdf_mlp_fwd")
+    return sdf, feat
+
+
+def make_raymarch(cam_pos, t_near, t_far, samples):
+    rm = RayMarch()
+    rm.cam_pos = (c_float * 3)(*[float(c) for c in cam_pos])
+    rm.t_near, rm.t_far, rm.samples_per_ray = float(t_near), float(t_far), int(samples)
+    return rm
+
+
+def render_sdf(ray_dirs, cam_pos, t_near, t_far, samples, A, trans, ws_cl, center, extend, packed,
+               pe_w=None, mode=None, frame_of_ray=None, rays_per_frame=0, want_xc=False, want_hit=True,
+               out_sdf=None):
+    """The fused render path: rays -> samples -> inverse LBS -> PE -> SDF MLP -> sdf [R,S] (+ first hit)."""
+    mode = DEFAULT_MLP_MODE if mode is None else mode
+    ray_dirs = ray_dirs.contiguous().float()
+    _check_input(ray_dirs, "ray_dirs")
+    A = A.contiguous().float()
+    trans = trans.contiguous().float()
+    R = ray_dirs.shape[0]
+    dev = ray_dirs.device
+    sdf = out_sdf if out_sdf is not None else torch.empty((R, samples), dtype=torch.float32, device=dev)
+    xc = torch.empty((R, samples, 3), dtype=torch.float32, device=dev) if want_xc else None
+    hit_idx = torch.empty((R,), dtype=torch.int32, device=dev) if want_hit else None
+    hit_t = torch.empty((R,), dtype=torch.float32, device=dev) if want_hit else None
+    if frame_of_ray is not None:
+        frame_of_ray = frame_of_ray.contiguous().to(torch.int32)
+    rm = make_raymarch(cam_pos, t_near, t_far, samples)
+    vox = make_voxel(ws_cl, center, extend)
+    with torch.cuda.device(dev):
+        check(_lib.load().recmv_render_sdf(_ptr(ray_dirs), byref(rm), _ptr(A), _ptr(trans),
+                                           _ptr(frame_of_ray), int(rays_per_frame), int(A.shape[0]),
+                                           byref(vox), _ptr(packed), _pe_array(pe_w), _ptr(sdf), _ptr(xc),
+                                           _ptr(hit_idx), _ptr(hit_t), R, mode, _stream(ray_dirs)),
+              "recmv_render_sdf")
+    return sdf, xc, hit_idx, hit_t
+
+
+def launch_count():
+    return int(_lib.load().recmv_launch_count())
