@@ -190,13 +190,23 @@ constexpr int kOutDim = 257;   // 1 + 256
 __host__ __device__ constexpr int layer_in(int l) { return l == 0 ? kPE : kHidden; }
 __host__ __device__ constexpr int layer_out(int l) { return l == 3 ? kSkipOut : (l == 8 ? kOutDim : kHidden); }
 
-// Packed weight blob layout (see sdf_pack.cu)
+// Packed weight blob layout (built by recmv_sdf_pack_weights, sdf_mlp_simt.cu).
+//  * fp32 transposed copies [K][Npad32] + padded biases: the FP32_SIMT kernel
+//  * fp16 hi/lo "panels" for tcgen05: the K dimension of every layer is cut into 64-wide blocks; a panel
+//    is [512 n][64 k] fp16 (128-byte rows = one TMA/UMMA swizzle row).  Panels of all layers are
+//    stacked, plane hi first then plane lo, so ONE 2-D tensor map [2*66*512 rows, 64 cols] serves every
+//    weight tile.  Layer 4 has 9 panels: 8 for the 473(+39 zero) hidden inputs and 1 for the
+//    positional-encoding inputs of the skip connection (its 1/sqrt2 folded into the weights).
+constexpr int kNumPanels = 66;
+__host__ __device__ constexpr int panel_base(int l) {
+  return l == 0 ? 0 : (l <= 4 ? 1 + 8 * (l - 1) : 34 + 8 * (l - 5));
+}
+__host__ __device__ constexpr int num_panels(int l) { return l == 0 ? 1 : (l == 4 ? 9 : 8); }
 struct PackedLayout {
-  size_t w32_off[kNumLayers];   // fp32 [out, in] row-major
-  size_t b32_off[kNumLayers];   // fp32 [out]
-  size_t f16_off[kNumLayers];   // fp16 planes: hi [Npad, Kpad] then lo [Npad, Kpad], K-major
-  size_t bpad_off[kNumLayers];  // fp32 [Npad] bias padded with zeros
-  int Npad[kNumLayers], Kpad[kNumLayers];
+  size_t w32_off[kNumLayers];   // fp32 [K, Npad32] (transposed) for the SIMT kernel
+  size_t b32_off[kNumLayers];   // fp32 [512] bias padded with zeros
+  size_t bias_all_off;          // == b32_off[0]; the 9 padded biases are contiguous, stride 512 floats
+  size_t f16_off;               // fp16 panels: [2 planes][66 panels][512][64]
   size_t total;
 };
 PackedLayout packed_layout();

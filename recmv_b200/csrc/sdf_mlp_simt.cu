@@ -17,44 +17,41 @@ namespace recmv {
 // ---------------------------------------------------------------------------------------------
 constexpr int kNpad32(int l) { return l == 8 ? 264 : 512; }
 constexpr int kKfull(int l) { return l == 0 ? kPE : 512; }
-constexpr int kKpadTc(int l) { return l == 0 ? 64 : (l == 4 ? 576 : 512); }
 
 PackedLayout packed_layout() {
   PackedLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
-  for (int l = 0; l < kNumLayers; ++l) {
-    L.w32_off[l] = take((size_t)kKfull(l) * kNpad32(l) * 4);
-    L.b32_off[l] = take(512 * 4);
-    L.bpad_off[l] = L.b32_off[l];
-    L.Npad[l] = 512;
-    L.Kpad[l] = kKpadTc(l);
-    L.f16_off[l] = take((size_t)2 * 512 * kKpadTc(l) * 2);
-  }
+  L.bias_all_off = take((size_t)kNumLayers * 512 * 4);
+  for (int l = 0; l < kNumLayers; ++l) L.b32_off[l] = L.bias_all_off + (size_t)l * 512 * 4;
+  for (int l = 0; l < kNumLayers; ++l) L.w32_off[l] = take((size_t)kKfull(l) * kNpad32(l) * 4);
+  L.f16_off = take((size_t)2 * kNumPanels * 512 * 64 * 2);
   L.total = off;
   return L;
 }
 
-// one thread per (n, k) of the padded fp16 planes and of the transposed fp32 copy
+// fp32 transposed copy + padded bias + fp16 hi/lo panels of one layer
 __global__ void __launch_bounds__(256) pack_layer_kernel(const float* __restrict__ W /*[out,in]*/,
                                                          const float* __restrict__ b, int l, int out,
                                                          int in, float* __restrict__ w32t, int npad32,
                                                          float* __restrict__ bpad,
-                                                         __half* __restrict__ hi, __half* __restrict__ lo,
-                                                         int kpad) {
+                                                         __half* __restrict__ planes) {
   const float scale = (l == 4) ? 0.70710678118654752440f : 1.f;  // cat([x, pe]) / sqrt(2) folded in
-  int64_t total = (int64_t)512 * kpad;
+  const int np = num_panels(l);
+  int64_t total = (int64_t)np * 512 * 64;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int n = (int)(i / kpad), k = (int)(i - (int64_t)n * kpad);
-    // source column of K index k
-    int src_k = k;
-    if (l == 4) src_k = k < 473 ? k : (k < 512 ? -1 : (k < 512 + kPE ? 473 + (k - 512) : -1));
-    else if (k >= in) src_k = -1;
+    int pi = (int)(i / (512 * 64));
+    int n = (int)((i / 64) % 512), kk = (int)(i % 64);
+    int src_k;
+    if (l == 0) src_k = kk < kPE ? kk : -1;
+    else if (l == 4) src_k = pi < 8 ? (pi * 64 + kk < kSkipOut ? pi * 64 + kk : -1) : (kk < kPE ? kSkipOut + kk : -1);
+    else src_k = pi * 64 + kk;
     float v = (n < out && src_k >= 0) ? W[(size_t)n * in + src_k] * scale : 0.f;
     __half h = __float2half_rn(v);
-    hi[i] = h;
-    lo[i] = __float2half_rn(v - __half2float(h));
+    size_t o = ((size_t)(panel_base(l) + pi) * 512 + n) * 64 + kk;
+    planes[o] = h;
+    planes[(size_t)kNumPanels * 512 * 64 + o] = __float2half_rn(v - __half2float(h));
   }
   int64_t total32 = (int64_t)in * npad32;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total32;
@@ -266,11 +263,9 @@ extern "C" int recmv_sdf_pack_weights(const float* W_all, const float* b_all, vo
   for (int l = 0; l < kNumLayers; ++l) {
     int in = layer_in(l), out = layer_out(l);
     char* base = (char*)packed;
-    __half* hi = (__half*)(base + L.f16_off[l]);
-    __half* lo = hi + (size_t)512 * L.Kpad[l];
-    pack_layer_kernel<<<stride_grid((int64_t)512 * L.Kpad[l], 256, 4), 256, 0, st>>>(
+    pack_layer_kernel<<<stride_grid((int64_t)num_panels(l) * 512 * 64, 256, 4), 256, 0, st>>>(
         W_all + woff, b_all + boff, l, out, in, (float*)(base + L.w32_off[l]), kNpad32(l),
-        (float*)(base + L.b32_off[l]), hi, lo, L.Kpad[l]);
+        (float*)(base + L.b32_off[l]), (__half*)(base + L.f16_off));
     int s = launch_status();
     if (s) return s;
     woff += (size_t)in * out;

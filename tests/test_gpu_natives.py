@@ -29,14 +29,15 @@ def test_minv3x3_forward_backward(dtype, tol, n):
     clear = (det.abs() - 1e-4).abs() > 1e-6 * (1 if dtype == torch.float32 else 1e-6)
     assert bool((ok.cpu() == ref_ok)[clear].all())
     both = ok.cpu() & ref_ok
-    scale = ref_inv[both].abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-6)
-    assert float(((inv.cpu()[both] - ref_inv[both]).abs() / scale).max()) < tol * 50
+    if both.any():
+        scale = ref_inv[both].abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-6)
+        assert float(((inv.cpu()[both] - ref_inv[both]).abs() / scale).max()) < tol * 50
     assert bool((inv.cpu()[~ok.cpu()] == 0).all())
     gr = torch.randn((n, 3, 3), generator=g, dtype=dtype)
     out = ops.minv3x3_backward(gr.to(DEV), inv)
     ref = ot.minv3x3_bwd(gr, inv.cpu())
     s = ref.abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-6)
-    assert float(((out.cpu() - ref).abs() / s).max()) < tol * 50
+    assert float(((out.cpu() - ref).abs() / s).amax()) < tol * 50
 
 
 def test_minv3x3_reference_check_script_property():
