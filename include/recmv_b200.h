@@ -136,6 +136,14 @@ RECMV_API int recmv_sdf_pack_weights(const float* W_all, const float* b_all, voi
 RECMV_API int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float* pe_w /*host*/,
                       float* out_sdf, float* out_feat, int64_t P, int mode, recmv_stream_t stream);
 
+/* Diagnostics for the tcgen05 path (used by tests/test_gpu_tc_bringup.py): same computation as
+ * recmv_sdf_mlp_fwd in a TC mode (passes = 1 or 3), plus status_host[4] = {code, barrier tag, block, 0}
+ * of the kernel's bounded mbarrier waits (code 0 = no wait timed out) and, when dbg_out != NULL, the raw
+ * fp32 accumulator (before bias) of layer dbg_layer for the first 128 points, [128][512].              */
+RECMV_API int recmv_sdf_mlp_tc_debug(const float* x, const void* packed, const float* pe_w /*host*/,
+                           float* out_sdf, float* out_feat, int64_t P, int passes, int dbg_layer,
+                           float* dbg_out, int* status_host /*host*/, recmv_stream_t stream);
+
 /* ---- the fused render path (BASELINE north star) -------------------------------------------------
  * One launch: ray r, sample k -> x_obs = cam_pos + t_k dir_r, t_k = t_near + (k+1/2)(t_far-t_near)/S
  * -> inverse LBS (frame = frame_of_ray[r] or r / rays_per_frame) -> PE -> SDF MLP -> sdf [R,S].

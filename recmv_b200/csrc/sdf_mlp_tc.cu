@@ -1,8 +1,399 @@
-// tcgen05 implementation of the fused SDF path (placeholder until the kernel lands).
+// tcgen05 implementation of the fused SDF path.  ONE persistent kernel: for every tile of 128 points
+// (64 per CTA of a 2-CTA cluster) it runs  [ray -> x_obs -> skinning-voxel sample -> inverse LBS ->]
+// positional encoding -> 9 linears (+softplus) -> sdf / 256 features  with every activation kept
+// on-chip.  Replaces model/Embedder.py:43-50 + model/network.py:89-119 (and, in render mode, the
+// Deformer.py:406-445 gather/blend and a FastMinv inverse) for the forward path.
+//
+// Mapping to the hardware (B200, sm_100a):
+//  * tensor cores: tcgen05.mma.cta_group::2.kind::f16, M = 128 over the CTA pair (64 rows per CTA --
+//    full tensor rate, and a 64x512 fp32 layer output takes only 256 of the 512 TMEM columns, so TWO
+//    layer accumulators fit and layer l+1's MMAs run while layer l's accumulator is still being drained),
+//    N = 256 per instruction (each CTA stages half of every weight tile => weight traffic from L2 is
+//    halved), K = 16.  fp32 parity mode (passes = 3): operands are split a = hi + lo in fp16 and every
+//    product is 3 MMAs (hi*hi + lo*hi + hi*lo), fp32 accumulation in TMEM.
+//  * weights: fp16 hi/lo panels streamed by TMA (128-byte swizzle) from L2 through a 5-slot x 16 KB ring,
+//    signalled with mbarrier complete_tx on the leader CTA, slots released by tcgen05.commit.
+//  * activations: 64 x 512 fp16 hi + lo (128 KB) in shared memory in the UMMA K-major SW128 layout,
+//    rewritten IN PLACE by the epilogue (the full layer output sits in TMEM first), K-block by K-block,
+//    each K-block released to the MMA warp through its own mbarrier so the next layer starts as soon as
+//    its first 64 inputs exist.
+//  * warp roles: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-7 epilogue (one TMEM
+//    lane quadrant each: tcgen05.ld -> bias -> softplus -> hi/lo split -> swizzled st.shared),
+//    8-9 prologue for the NEXT tile (point fetch / inverse LBS / positional encoding).
+// Every mbarrier wait is bounded: a protocol bug surfaces as a status code, not a hung GPU.
 #include "sdf_mlp.cuh"
+#include "tc_common.cuh"
+
 namespace recmv {
-int tc_sdf_forward(const PointSource&, const void*, const PeWeights&, float*, float*, int64_t, int,
-                   cudaStream_t) {
-  return RECMV_E_UNSUPPORTED;
+using namespace tc;
+
+namespace {
+
+constexpr int kThreads = 320;
+constexpr int kRowsPerCta = 64;
+constexpr int kSlots = 5;
+constexpr uint32_t kSlotBytes = 16384;
+// shared memory map (offsets from a 1024-aligned base)
+constexpr uint32_t kOffAHi = 0;
+constexpr uint32_t kOffALo = 65536;
+constexpr uint32_t kOffPeHi = 131072;
+constexpr uint32_t kOffPeLo = 139264;
+constexpr uint32_t kOffW = 147456;
+constexpr uint32_t kOffBar = kOffW + kSlots * kSlotBytes;  // 229376
+// barrier indices (8 bytes each)
+constexpr int kBarFull = 0;      // [5] leader: weight slot filled (2 arrivals + tx bytes of both CTAs)
+constexpr int kBarEmpty = 5;     // [5] local : weight slot consumed (tcgen05.commit multicast)
+constexpr int kBarAReady = 10;   // [8] leader: activation K-block written by both CTAs (4 warp arrivals)
+constexpr int kBarPeReady = 18;  //     leader: positional-encoding block written (4 warp arrivals)
+constexpr int kBarPeFree = 19;   //     local : layer-4 MMAs done with the PE block (commit multicast)
+constexpr int kBarAccFull = 20;  // [2] local : layer accumulator complete (commit multicast)
+constexpr int kBarAccEmpty = 22; // [2] leader: accumulator drained by all 8 epilogue warps of the pair
+constexpr int kNumBars = 24;
+constexpr uint32_t kOffMisc = kOffBar + kNumBars * 8;  // tmem ptr, abort flag, valid flags
+constexpr uint32_t kSmemBytes = kOffMisc + 16 + 128 + 1024 /*alignment slack*/;
+
+struct TcParams {
+  PointSource src;
+  PeWeights pw;
+  const float* bias;  // [9][512] padded
+  float* out_sdf;
+  float* out_feat;
+  long long P;
+  int passes;
+  DevStatus* status;
+  // diagnostics: raw accumulator (before bias) of layer dbg_layer for tile 0 -> dbg_out [128][512]
+  int dbg_layer;
+  float* dbg_out;
+};
+
+// K-block processing order of a layer's input: the epilogue produces K-blocks pairwise {0,2},{1,3},...
+// (two lane halves of the TMEM layout work in parallel); the skip layer starts with the PE block, which
+// is ready long before.
+__device__ __forceinline__ int kb_order(int l, int i) {
+  if (l == 0) return 0;
+  if (l == 4) {
+    if (i == 0) return 8;
+    --i;
+  }
+  return (i & 4) | ((i & 1) << 1) | ((i >> 1) & 1);  // 0,2,1,3,4,6,5,7
 }
+
+}  // namespace
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap16,
+              const TcParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kOffBar;
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(gbase + kOffMisc + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kOffMisc);
+  volatile unsigned char* valid = reinterpret_cast<volatile unsigned char*>(gbase + kOffMisc + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const long long num_tiles = (prm.P + 127) / 128;
+  const long long cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int passes = prm.passes;
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int s = 0; s < kSlots; ++s) { mbar_init(BAR(kBarFull + s), 2); mbar_init(BAR(kBarEmpty + s), 1); }
+    for (int k = 0; k < 8; ++k) mbar_init(BAR(kBarAReady + k), 4);
+    mbar_init(BAR(kBarPeReady), 4);
+    mbar_init(BAR(kBarPeFree), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 1); mbar_init(BAR(kBarAccEmpty + b), 8); }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmap128); prefetch_tmap(&tmap16); }
+  if (warp == 2) tmem_alloc_pair(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ==================================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ring = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int l = 0; l < kNumLayers; ++l) {
+          const int nkb = num_panels(l);
+          for (int i = 0; i < nkb; ++i) {
+            const int kbi = kb_order(l, i);
+            for (int nt = 0; nt < 2; ++nt) {
+              const bool small = (l == 8 && nt == 1);
+              for (int plane = 0; plane < (passes == 3 ? 2 : 1); ++plane) {
+                mbar_wait(BAR(kBarEmpty + slot), ring ^ 1u, abort_flag, prm.status, 100 + slot);
+                const uint32_t bytes = small ? 16u * 128u : 128u * 128u;
+                mbar_expect_tx_cluster(BAR(kBarFull + slot), 0, bytes);
+                const int row = (plane * kNumPanels + panel_base(l) + kbi) * 512 +
+                                (small ? 256 + (int)rank * 16 : nt * 256 + (int)rank * 128);
+                tma_load_2d_pair(base + kOffW + slot * kSlotBytes, small ? (const void*)&tmap16 : (const void*)&tmap128,
+                                 mapa(BAR(kBarFull + slot), 0), 0, row);
+                if (++slot == kSlots) { slot = 0; ring ^= 1u; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader CTA only) =================================
+    if (leader && lane == 0) {
+      int slot = 0;
+      uint32_t ring = 0;
+      long long it = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        for (int l = 0; l < kNumLayers; ++l) {
+          const long long L = it * kNumLayers + l;
+          const int buf = (int)(L & 1);
+          const uint32_t use = (uint32_t)(L >> 1);
+          mbar_wait(BAR(kBarAccEmpty + buf), (use & 1u) ^ 1u, abort_flag, prm.status, 200 + buf);
+          tc_fence_after();
+          const int nkb = num_panels(l);
+          for (int i = 0; i < nkb; ++i) {
+            const int kbi = kb_order(l, i);
+            const bool is_pe = (l == 0) || (l == 4 && kbi == 8);
+            if (l == 0) mbar_wait(BAR(kBarPeReady), (uint32_t)(it & 1), abort_flag, prm.status, 210);
+            if (!is_pe) mbar_wait(BAR(kBarAReady + kbi), (uint32_t)((l - 1) & 1), abort_flag, prm.status, 220 + kbi);
+            tc_fence_after();
+            const uint64_t a_hi = smem_desc_sw128(is_pe ? base + kOffPeHi : base + kOffAHi + kbi * 8192);
+            const uint64_t a_lo = smem_desc_sw128(is_pe ? base + kOffPeLo : base + kOffALo + kbi * 8192);
+            for (int nt = 0; nt < 2; ++nt) {
+              const bool small = (l == 8 && nt == 1);
+              const uint32_t idesc = small ? idesc_f16(128, 32) : idesc_f16(128, 256);
+              const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + nt * 128);
+              mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 230 + slot);
+              tc_fence_after();
+              uint64_t b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              if (passes == 3) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_lo + 2 * k, b + 2 * k, idesc, 1u);
+              }
+              umma_commit_pair(BAR(kBarEmpty + slot), 3);
+              if (++slot == kSlots) { slot = 0; ring ^= 1u; }
+              if (passes == 3) {
+                mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 240 + slot);
+                tc_fence_after();
+                b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, 1u);
+                umma_commit_pair(BAR(kBarEmpty + slot), 3);
+                if (++slot == kSlots) { slot = 0; ring ^= 1u; }
+              }
+            }
+          }
+          umma_commit_pair(BAR(kBarAccFull + buf), 3);
+          if (l == 4) umma_commit_pair(BAR(kBarPeFree), 3);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================ epilogue (both CTAs) =========================================
+    const int q = warp - 4;            // TMEM lane quadrant == warp index % 4
+    const int row = (q & 1) * 32 + lane;  // tile row owned by this thread (lanes 64.. mirror rows 0..63)
+    const int half = q >> 1;           // which 128-column half of each 256-wide N tile
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    long long it = 0;
+    for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const long long p = tile * 128 + (long long)rank * kRowsPerCta + row;
+      for (int l = 0; l < kNumLayers; ++l) {
+        const long long L = it * kNumLayers + l;
+        const int buf = (int)(L & 1);
+        const uint32_t use = (uint32_t)(L >> 1);
+        mbar_wait(BAR(kBarAccFull + buf), use & 1u, abort_flag, prm.status, 300 + q);
+        tc_fence_after();
+        const float* bias = prm.bias + l * 512;
+        for (int nt = 0; nt < 2; ++nt) {
+          const bool small = (l == 8 && nt == 1);
+          const int ncol = small ? 32 : 128;  // (only 16 of the 32 are real for the small tile)
+          for (int c0 = 0; c0 < ncol; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + lane_addr + (uint32_t)(buf * 256 + nt * 128 + c0), r);
+            tmem_ld_wait();
+            const int f0 = small ? 256 + half * 16 + c0 : nt * 256 + half * 128 + c0;
+            if (prm.dbg_out && prm.dbg_layer == l && tile == 0 && !small) {
+              float* d = prm.dbg_out + ((size_t)rank * kRowsPerCta + row) * 512 + f0;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(r[c]);
+            }
+            if (l < 8) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int f = f0 + 8 * j;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + f));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + f + 4));
+                float v[8] = {__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y,
+                              __uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w,
+                              __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
+                              __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = softplus100(v[e]);
+                uint4 hi, lo;
+                split8(v, hi, lo);
+                const int kb = f >> 6, chunk = (f & 63) >> 3;
+                const uint32_t off = (uint32_t)kb * 8192u + sw128_offset(row, chunk);
+                st_shared_v4(base + kOffAHi + off, hi);
+                st_shared_v4(base + kOffALo + off, lo);
+              }
+              if ((c0 & 32) != 0) {  // a 64-wide K block of the next layer's input is complete
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(BAR(kBarAReady + (f0 >> 6)), 0);
+              }
+            } else if (p < prm.P) {
+              // last layer: column 0 = sdf, columns 1..256 = features
+              const bool ok = valid[(it & 1) * 64 + row] != 0;
+              if (!small) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  const int f = f0 + c;
+                  const float v = __uint_as_float(r[c]) + __ldg(bias + f);
+                  if (f == 0) prm.out_sdf[p] = ok ? v : kInvalidSdf;
+                  else if (prm.out_feat) prm.out_feat[p * 256 + (f - 1)] = v;
+                }
+              } else if (half == 0 && c0 == 0 && prm.out_feat) {
+                prm.out_feat[p * 256 + 255] = __uint_as_float(r[0]) + __ldg(bias + 256);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(BAR(kBarAccEmpty + buf), 0);
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================ prologue for the next tile (both CTAs) ========================
+    const int row = (warp - 8) * 32 + lane;
+    long long it = 0;
+    for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const long long p = tile * 128 + (long long)rank * kRowsPerCta + row;
+      float pe[40];
+      bool ok = true;
+      if (p < prm.P) {
+        float cx, cy, cz;
+        ok = fetch_point(prm.src, p, cx, cy, cz);
+        positional_encode(cx, cy, cz, prm.pw.w, pe);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 39; ++e) pe[e] = 0.f;
+      }
+      pe[39] = 0.f;
+      if (it > 0) mbar_wait(BAR(kBarPeFree), (uint32_t)((it - 1) & 1), abort_flag, prm.status, 400);
+      const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int chunk = 0; chunk < 8; ++chunk) {
+        uint4 hi = zero, lo = zero;
+        if (chunk < 5) split8(pe + 8 * chunk, hi, lo);
+        const uint32_t off = sw128_offset(row, chunk);
+        st_shared_v4(base + kOffPeHi + off, hi);
+        st_shared_v4(base + kOffPeLo + off, lo);
+      }
+      valid[(it & 1) * 64 + row] = ok ? 1 : 0;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(BAR(kBarPeReady), 0);
+    }
+  }
+
+  // ---- teardown: every role has drained; both CTAs must be done before TMEM goes away ---------------
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
+namespace {
+struct TmapCache {
+  const void* base = nullptr;
+  CUtensorMap m128, m16;
+};
+DevStatus* g_status = nullptr;  // one device-side status record per process (device 0..n share: reset per launch)
+}  // namespace
+
+static int launch_tc(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
+                     float* out_feat, int64_t P, int passes, int dbg_layer, float* dbg_out, int* status_host,
+                     cudaStream_t st) {
+  if (passes != 1 && passes != 3) return RECMV_E_DTYPE;
+  PackedLayout L = packed_layout();
+  const char* pb = (const char*)packed;
+  static TmapCache cache[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  TmapCache& tc_ = cache[dev & 15];
+  const void* panels = pb + L.f16_off;
+  if (tc_.base != panels) {
+    int s = make_panel_tmap(&tc_.m128, panels, (uint64_t)2 * kNumPanels * 512, 128);
+    if (s) return s;
+    s = make_panel_tmap(&tc_.m16, panels, (uint64_t)2 * kNumPanels * 512, 16);
+    if (s) return s;
+    tc_.base = panels;
+  }
+  static bool attr_done[16] = {false};
+  if (!attr_done[dev & 15]) {
+    cudaError_t e = cudaFuncSetAttribute(sdf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_done[dev & 15] = true;
+  }
+  static DevStatus* status_dev[16] = {nullptr};
+  if (!status_dev[dev & 15]) {
+    cudaError_t e = cudaMalloc(&status_dev[dev & 15], sizeof(DevStatus));
+    if (e != cudaSuccess) return (int)e;
+  }
+  DevStatus* sd = status_dev[dev & 15];
+  cudaMemsetAsync(sd, 0, sizeof(DevStatus), st);
+  TcParams prm;
+  prm.src = src; prm.pw = pw;
+  prm.bias = (const float*)(pb + L.bias_all_off);
+  prm.out_sdf = out_sdf; prm.out_feat = out_feat; prm.P = P; prm.passes = passes; prm.status = sd;
+  prm.dbg_layer = dbg_layer; prm.dbg_out = dbg_out;
+  int64_t tiles = (P + 127) / 128;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = (int)tiles;
+  sdf_tc_kernel<<<clusters * 2, kThreads, kSmemBytes, st>>>(tc_.m128, tc_.m16, prm);
+  int s = launch_status();
+  if (s) return s;
+  if (status_host) {  // diagnostics path: synchronous read-back of the device status
+    DevStatus h;
+    cudaError_t e = cudaMemcpyAsync(&h, sd, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return (int)e;
+    status_host[0] = h.code; status_host[1] = h.detail; status_host[2] = h.block; status_host[3] = 0;
+  }
+  return RECMV_OK;
+}
+
+int tc_sdf_forward(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
+                   float* out_feat, int64_t P, int passes, cudaStream_t st) {
+  return launch_tc(src, packed, pw, out_sdf, out_feat, P, passes, -1, nullptr, nullptr, st);
+}
+
 }  // namespace recmv
+
+using namespace recmv;
+
+// Diagnostics entry (see include/recmv_b200.h): runs the tcgen05 path on canonical points and returns
+// the device status record (which bounded wait timed out, if any) plus the raw accumulator of one layer.
+extern "C" int recmv_sdf_mlp_tc_debug(const float* x, const void* packed, const float* pe_w, float* out_sdf,
+                                      float* out_feat, int64_t P, int passes, int dbg_layer, float* dbg_out,
+                                      int* status_host, recmv_stream_t stream) {
+  if (P <= 0) return RECMV_E_SHAPE;
+  if (!x || !packed || !pe_w || !out_sdf || !status_host) return RECMV_E_NULL;
+  PointSource src = {};
+  src.x = x;
+  src.S = 1;
+  PeWeights pw;
+  for (int i = 0; i < 12; ++i) pw.w[i] = pe_w[i];
+  return launch_tc(src, packed, pw, out_sdf, out_feat, P, passes, dbg_layer, dbg_out, status_host,
+                   (cudaStream_t)stream);
+}
