@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--mode", default=os.environ.get("RECMV_BENCH_MODE", "simt"), choices=sorted(MODES))
+    ap.add_argument("--mode", default=os.environ.get("RECMV_BENCH_MODE", "tc3"), choices=sorted(MODES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -198,6 +198,13 @@ __host__ __device__ constexpr int layer_out(int l) { return l == 3 ? kSkipOut : 
 //    weight tile.  Layer 4 has 9 panels: 8 for the 473(+39 zero) hidden inputs and 1 for the
 //    positional-encoding inputs of the skip connection (its 1/sqrt2 folded into the weights).
 constexpr int kNumPanels = 66;
+// Exact power-of-two operand scaling of the tcgen05 path: activations are stored as fp16(hi)+fp16(lo) of
+// 2^6 * a, weights of 2^10 * w, so the `lo` residuals (~2^-12 of the value) stay in fp16's NORMAL range
+// (unscaled they are subnormal whenever |value| < 0.125 and carry only ~2^-20 relative precision);
+// the epilogue multiplies the fp32 accumulator by 2^-16.  Range: |a| < 1023, |w| < 63.9.
+constexpr float kActScale = 64.f;
+constexpr float kWgtScale = 1024.f;
+constexpr float kAccUnscale = 1.f / (64.f * 1024.f);
 __host__ __device__ constexpr int panel_base(int l) {
   return l == 0 ? 0 : (l <= 4 ? 1 + 8 * (l - 1) : 34 + 8 * (l - 5));
 }

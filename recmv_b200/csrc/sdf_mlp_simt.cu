@@ -48,10 +48,11 @@ __global__ void __launch_bounds__(256) pack_layer_kernel(const float* __restrict
     else if (l == 4) src_k = pi < 8 ? (pi * 64 + kk < kSkipOut ? pi * 64 + kk : -1) : (kk < kPE ? kSkipOut + kk : -1);
     else src_k = pi * 64 + kk;
     float v = (n < out && src_k >= 0) ? W[(size_t)n * in + src_k] * scale : 0.f;
-    __half h = __float2half_rn(v);
+    const float vs = v * kWgtScale;
+    __half h = __float2half_rn(vs);
     size_t o = ((size_t)(panel_base(l) + pi) * 512 + n) * 64 + kk;
     planes[o] = h;
-    planes[(size_t)kNumPanels * 512 * 64 + o] = __float2half_rn(v - __half2float(h));
+    planes[(size_t)kNumPanels * 512 * 64 + o] = __float2half_rn(vs - __half2float(h));
   }
   int64_t total32 = (int64_t)in * npad32;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total32;

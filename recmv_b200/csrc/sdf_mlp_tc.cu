@@ -223,7 +223,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
             if (prm.dbg_out && prm.dbg_layer == l && tile == 0 && !small) {
               float* d = prm.dbg_out + ((size_t)rank * kRowsPerCta + row) * 512 + f0;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(r[c]);
+              for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(r[c]) * kAccUnscale;
             }
             if (l < 8) {
 #pragma unroll
@@ -231,12 +231,12 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
                 const int f = f0 + 8 * j;
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + f));
                 const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + f + 4));
-                float v[8] = {__uint_as_float(r[8 * j + 0]) + b0.x, __uint_as_float(r[8 * j + 1]) + b0.y,
-                              __uint_as_float(r[8 * j + 2]) + b0.z, __uint_as_float(r[8 * j + 3]) + b0.w,
-                              __uint_as_float(r[8 * j + 4]) + b1.x, __uint_as_float(r[8 * j + 5]) + b1.y,
-                              __uint_as_float(r[8 * j + 6]) + b1.z, __uint_as_float(r[8 * j + 7]) + b1.w};
+                float v[8] = {fmaf(__uint_as_float(r[8 * j + 0]), kAccUnscale, b0.x), fmaf(__uint_as_float(r[8 * j + 1]), kAccUnscale, b0.y),
+                              fmaf(__uint_as_float(r[8 * j + 2]), kAccUnscale, b0.z), fmaf(__uint_as_float(r[8 * j + 3]), kAccUnscale, b0.w),
+                              fmaf(__uint_as_float(r[8 * j + 4]), kAccUnscale, b1.x), fmaf(__uint_as_float(r[8 * j + 5]), kAccUnscale, b1.y),
+                              fmaf(__uint_as_float(r[8 * j + 6]), kAccUnscale, b1.z), fmaf(__uint_as_float(r[8 * j + 7]), kAccUnscale, b1.w)};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = softplus100(v[e]);
+                for (int e = 0; e < 8; ++e) v[e] = softplus100(v[e]) * kActScale;
                 uint4 hi, lo;
                 split8(v, hi, lo);
                 const int kb = f >> 6, chunk = (f & 63) >> 3;
@@ -256,12 +256,12 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                   const int f = f0 + c;
-                  const float v = __uint_as_float(r[c]) + __ldg(bias + f);
+                  const float v = fmaf(__uint_as_float(r[c]), kAccUnscale, __ldg(bias + f));
                   if (f == 0) prm.out_sdf[p] = ok ? v : kInvalidSdf;
                   else if (prm.out_feat) prm.out_feat[p * 256 + (f - 1)] = v;
                 }
               } else if (half == 0 && c0 == 0 && prm.out_feat) {
-                prm.out_feat[p * 256 + 255] = __uint_as_float(r[0]) + __ldg(bias + 256);
+                prm.out_feat[p * 256 + 255] = fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias + 256));
               }
             }
           }
@@ -283,6 +283,8 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
         float cx, cy, cz;
         ok = fetch_point(prm.src, p, cx, cy, cz);
         positional_encode(cx, cy, cz, prm.pw.w, pe);
+#pragma unroll
+        for (int e = 0; e < 39; ++e) pe[e] *= kActScale;
       } else {
 #pragma unroll
         for (int e = 0; e < 39; ++e) pe[e] = 0.f;

@@ -67,8 +67,9 @@ def main():
             rc, st, sdf, feat, dbg = run_debug(xd, packed, 128, passes, layer)
             raw = (pre[layer] - bs[layer])  # accumulator excludes the bias
             n = raw.shape[1]
-            got = dbg[:, :min(n, 512)].double().cpu()
-            ref = raw[:, :min(n, 512)]
+            nc = min(n, 512) if layer < 8 else 256
+            got = dbg[:, :nc].double().cpu()
+            ref = raw[:, :nc]
             err = (got - ref).abs()
             finite = torch.isfinite(got)
             say(f"passes={passes} layer={layer} rc={rc} status={st} finite={finite.float().mean():.3f} "
@@ -76,8 +77,9 @@ def main():
                 f"ref_absmax={ref.abs().max():.3e}")
             if not finite.all() or err[finite].max() > 1e-2 * ref.abs().max():
                 # locate the structure of the mismatch: per 64-row x 64-col block
-                blk = err.nan_to_num(1e9).view(2, 64, -1, 64).amax(dim=(1, 3)) if n >= 64 else err
-                say("  block max err (rows 0-63 / 64-127 x 64-col blocks):", blk.tolist() if n >= 64 else "")
+                nn_ = (min(n, 512) // 64) * 64
+                blk = err[:, :nn_].nan_to_num(1e9).reshape(2, 64, -1, 64).amax(dim=(1, 3))
+                say("  block max err (rows 0-63 / 64-127 x 64-col blocks):", [[f"{v:.1e}" for v in r] for r in blk.tolist()])
                 dumps[f"p{passes}_l{layer}_got"] = got.numpy()
                 dumps[f"p{passes}_l{layer}_ref"] = ref.numpy()
         rc, st, sdf, feat, _ = run_debug(xd, packed, 4096, passes, -1)
