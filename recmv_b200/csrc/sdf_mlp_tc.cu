@@ -17,9 +17,9 @@
 //    rewritten IN PLACE by the epilogue (the full layer output sits in TMEM first), K-block by K-block,
 //    each K-block released to the MMA warp through its own mbarrier so the next layer starts as soon as
 //    its first 64 inputs exist.
-//  * warp roles: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-7 epilogue (one TMEM
-//    lane quadrant each: tcgen05.ld -> bias -> softplus -> hi/lo split -> swizzled st.shared),
-//    8-9 prologue for the NEXT tile (point fetch / inverse LBS / positional encoding).
+//  * warp roles: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-11 epilogue (two warps per
+//    TMEM lane quadrant, one 64-column K block each: tcgen05.ld -> bias -> softplus -> hi/lo split ->
+//    swizzled st.shared), 12-13 prologue for the NEXT tile (point fetch / inverse LBS / PE).
 // Every mbarrier wait is bounded: a protocol bug surfaces as a status code, not a hung GPU.
 #include "sdf_mlp.cuh"
 #include "tc_common.cuh"
@@ -29,7 +29,8 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 448;  // 4 role warps + 8 epilogue warps + 2 prologue warps
+constexpr int kEpiWarps = 8;
 constexpr int kRowsPerCta = 64;
 constexpr int kSlots = 5;
 constexpr uint32_t kSlotBytes = 16384;
@@ -47,7 +48,7 @@ constexpr int kBarAReady = 10;   // [8] leader: activation K-block written by bo
 constexpr int kBarPeReady = 18;  //     leader: positional-encoding block written (4 warp arrivals)
 constexpr int kBarPeFree = 19;   //     local : layer-4 MMAs done with the PE block (commit multicast)
 constexpr int kBarAccFull = 20;  // [2] local : layer accumulator complete (commit multicast)
-constexpr int kBarAccEmpty = 22; // [2] leader: accumulator drained by all 8 epilogue warps of the pair
+constexpr int kBarAccEmpty = 22; // [2] leader: accumulator drained by all 16 epilogue warps of the pair
 constexpr int kNumBars = 24;
 constexpr uint32_t kOffMisc = kOffBar + kNumBars * 8;  // tmem ptr, abort flag, valid flags
 constexpr uint32_t kSmemBytes = kOffMisc + 16 + 128 + 1024 /*alignment slack*/;
@@ -66,16 +67,21 @@ struct TcParams {
   float* dbg_out;
 };
 
-// K-block processing order of a layer's input: the epilogue produces K-blocks pairwise {0,2},{1,3},...
-// (two lane halves of the TMEM layout work in parallel); the skip layer starts with the PE block, which
-// is ready long before.
+// K-block processing order of a layer's input: the 8 epilogue warps release K blocks 0-3 (first N tile)
+// then 4-7 together; the skip layer starts with the PE block, which is ready long before.
 __device__ __forceinline__ int kb_order(int l, int i) {
   if (l == 0) return 0;
-  if (l == 4) {
-    if (i == 0) return 8;
-    --i;
-  }
-  return (i & 4) | ((i & 1) << 1) | ((i >> 1) & 1);  // 0,2,1,3,4,6,5,7
+  if (l == 4) return i == 0 ? 8 : i - 1;
+  return i;
+}
+
+// softplus(beta=100, threshold=20) on the MUFU pipe: ex2.approx / lg2.approx (2^-21-grade), 8-way ILP at
+// the call site.  (Accurate expf/log1pf cost ~60 dependent instructions per activation.)
+__device__ __forceinline__ float softplus100_fast(float z) {
+  const float t = 100.f * z;
+  const float e = __expf(fminf(t, 20.f));
+  const float y = __logf(1.f + e) * 0.01f;
+  return t > 20.f ? z : y;
 }
 
 }  // namespace
@@ -105,7 +111,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
     for (int k = 0; k < 8; ++k) mbar_init(BAR(kBarAReady + k), 4);
     mbar_init(BAR(kBarPeReady), 4);
     mbar_init(BAR(kBarPeFree), 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 1); mbar_init(BAR(kBarAccEmpty + b), 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 1); mbar_init(BAR(kBarAccEmpty + b), 2 * kEpiWarps); }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmap128); prefetch_tmap(&tmap16); }
@@ -196,11 +202,12 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ================================ epilogue (both CTAs) =========================================
-    const int q = warp - 4;            // TMEM lane quadrant == warp index % 4
+    const int q = warp & 3;               // TMEM lane quadrant == warp index % 4
+    const int grp = (warp - 4) >> 2;      // which 64-column K block of this quadrant's 128-column half
     const int row = (q & 1) * 32 + lane;  // tile row owned by this thread (lanes 64.. mirror rows 0..63)
-    const int half = q >> 1;           // which 128-column half of each 256-wide N tile
+    const int half = q >> 1;              // which 128-column half of each 256-wide N tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     long long it = 0;
     for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -214,8 +221,9 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
         const float* bias = prm.bias + l * 512;
         for (int nt = 0; nt < 2; ++nt) {
           const bool small = (l == 8 && nt == 1);
-          const int ncol = small ? 32 : 128;  // (only 16 of the 32 are real for the small tile)
-          for (int c0 = 0; c0 < ncol; c0 += 32) {
+          if (small && grp != 0) continue;  // the 32-wide tail tile has a single 16-column group per half
+          for (int cc = 0; cc < (small ? 32 : 64); cc += 32) {
+            const int c0 = small ? cc : grp * 64 + cc;
             uint32_t r[32];
             tmem_ld32(tmem_base + lane_addr + (uint32_t)(buf * 256 + nt * 128 + c0), r);
             tmem_ld_wait();
@@ -236,7 +244,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
                               fmaf(__uint_as_float(r[8 * j + 4]), kAccUnscale, b1.x), fmaf(__uint_as_float(r[8 * j + 5]), kAccUnscale, b1.y),
                               fmaf(__uint_as_float(r[8 * j + 6]), kAccUnscale, b1.z), fmaf(__uint_as_float(r[8 * j + 7]), kAccUnscale, b1.w)};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = softplus100(v[e]) * kActScale;
+                for (int e = 0; e < 8; ++e) v[e] = softplus100_fast(v[e]) * kActScale;
                 uint4 hi, lo;
                 split8(v, hi, lo);
                 const int kb = f >> 6, chunk = (f & 63) >> 3;
@@ -244,7 +252,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
                 st_shared_v4(base + kOffAHi + off, hi);
                 st_shared_v4(base + kOffALo + off, lo);
               }
-              if ((c0 & 32) != 0) {  // a 64-wide K block of the next layer's input is complete
+              if (cc == 32) {  // this warp's 64-wide K block of the next layer's input is complete
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(BAR(kBarAReady + (f0 >> 6)), 0);
@@ -253,12 +261,13 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
               // last layer: column 0 = sdf, columns 1..256 = features
               const bool ok = valid[(it & 1) * 64 + row] != 0;
               if (!small) {
+                if (f0 == 0) prm.out_sdf[p] = ok ? fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias)) : kInvalidSdf;
+                if (prm.out_feat) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                  const int f = f0 + c;
-                  const float v = fmaf(__uint_as_float(r[c]), kAccUnscale, __ldg(bias + f));
-                  if (f == 0) prm.out_sdf[p] = ok ? v : kInvalidSdf;
-                  else if (prm.out_feat) prm.out_feat[p * 256 + (f - 1)] = v;
+                  for (int c = 0; c < 32; ++c) {
+                    const int f = f0 + c;
+                    if (f > 0) prm.out_feat[p * 256 + (f - 1)] = fmaf(__uint_as_float(r[c]), kAccUnscale, __ldg(bias + f));
+                  }
                 }
               } else if (half == 0 && c0 == 0 && prm.out_feat) {
                 prm.out_feat[p * 256 + 255] = fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias + 256));
@@ -271,9 +280,9 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
         if (lane == 0) mbar_arrive_cluster(BAR(kBarAccEmpty + buf), 0);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 4 + kEpiWarps) {
     // ================================ prologue for the next tile (both CTAs) ========================
-    const int row = (warp - 8) * 32 + lane;
+    const int row = (warp - 4 - kEpiWarps) * 32 + lane;
     long long it = 0;
     for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const long long p = tile * 128 + (long long)rank * kRowsPerCta + row;

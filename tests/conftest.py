@@ -40,3 +40,11 @@ def rel_err(a, b, scale):
     a = torch.as_tensor(a, dtype=torch.float64).cpu()
     b = torch.as_tensor(b, dtype=torch.float64).cpu()
     return float(((a - b).abs() / b.abs().clamp_min(scale)).max())
+
+
+def norm_err(a, b):
+    """max |a-b| / rms(b): error relative to the scale of the reference output (the north star's
+    'relative fp32' for a vector of outputs; robust where individual values cross zero)."""
+    a = torch.as_tensor(a, dtype=torch.float64).detach().cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).detach().cpu()
+    return float((a - b).abs().max() / b.pow(2).mean().sqrt())
