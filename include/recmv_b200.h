@@ -142,7 +142,9 @@ RECMV_API int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float*
  * fp32 accumulator (before bias) of layer dbg_layer for the first 128 points, [128][512].              */
 RECMV_API int recmv_sdf_mlp_tc_debug(const float* x, const void* packed, const float* pe_w /*host*/,
                            float* out_sdf, float* out_feat, int64_t P, int passes, int dbg_layer,
-                           float* dbg_out, int* status_host /*host*/, recmv_stream_t stream);
+                           float* dbg_out, int* status_host /*host*/,
+                           unsigned long long* trace /*device [4][2][9][16] clock stamps or NULL*/,
+                           recmv_stream_t stream);
 
 /* ---- the fused render path (BASELINE north star) -------------------------------------------------
  * One launch: ray r, sample k -> x_obs = cam_pos + t_k dir_r, t_k = t_near + (k+1/2)(t_far-t_near)/S

@@ -65,7 +65,15 @@ struct TcParams {
   // diagnostics: raw accumulator (before bias) of layer dbg_layer for tile 0 -> dbg_out [128][512]
   int dbg_layer;
   float* dbg_out;
+  // diagnostics: clock64 stamps of cluster 0 / leader CTA, tiles 0-1: trace[role][it][layer][16]
+  // role 0 = MMA thread, 1 = first epilogue warp, 2 = last epilogue warp, 3 = producer
+  unsigned long long* trace;
 };
+#define TRACE(role, it, l, ev)                                                                     \
+  do {                                                                                             \
+    if (prm.trace && blockIdx.x == 0 && (it) < 2)                                                  \
+      prm.trace[((((role) * 2 + (it)) * 9 + (l)) << 4) + (ev)] = (unsigned long long)clock64();     \
+  } while (0)
 
 // K-block processing order of a layer's input: the 8 epilogue warps release K blocks 0-3 (first N tile)
 // then 4-7 together; the skip layer starts with the PE block, which is ready long before.
@@ -127,11 +135,14 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
     if (lane == 0) {
       int slot = 0;
       uint32_t ring = 0;
-      for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      long long it = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         for (int l = 0; l < kNumLayers; ++l) {
           const int nkb = num_panels(l);
+          TRACE(3, it, l, 0);
           for (int i = 0; i < nkb; ++i) {
             const int kbi = kb_order(l, i);
+            if (i == nkb - 1) TRACE(3, it, l, 1);
             for (int nt = 0; nt < 2; ++nt) {
               const bool small = (l == 8 && nt == 1);
               for (int plane = 0; plane < (passes == 3 ? 2 : 1); ++plane) {
@@ -160,8 +171,10 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
           const long long L = it * kNumLayers + l;
           const int buf = (int)(L & 1);
           const uint32_t use = (uint32_t)(L >> 1);
+          TRACE(0, it, l, 0);
           mbar_wait(BAR(kBarAccEmpty + buf), (use & 1u) ^ 1u, abort_flag, prm.status, 200 + buf);
           tc_fence_after();
+          TRACE(0, it, l, 1);
           const int nkb = num_panels(l);
           for (int i = 0; i < nkb; ++i) {
             const int kbi = kb_order(l, i);
@@ -169,6 +182,9 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
             if (l == 0) mbar_wait(BAR(kBarPeReady), (uint32_t)(it & 1), abort_flag, prm.status, 210);
             if (!is_pe) mbar_wait(BAR(kBarAReady + kbi), (uint32_t)((l - 1) & 1), abort_flag, prm.status, 220 + kbi);
             tc_fence_after();
+            if (i == 0) TRACE(0, it, l, 2);
+            if (i == 4) TRACE(0, it, l, 3);
+            if (i == nkb - 1) TRACE(0, it, l, 4);
             const uint64_t a_hi = smem_desc_sw128(is_pe ? base + kOffPeHi : base + kOffAHi + kbi * 8192);
             const uint64_t a_lo = smem_desc_sw128(is_pe ? base + kOffPeLo : base + kOffALo + kbi * 8192);
             for (int nt = 0; nt < 2; ++nt) {
@@ -198,6 +214,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
             }
           }
           umma_commit_pair(BAR(kBarAccFull + buf), 3);
+          TRACE(0, it, l, 5);
           if (l == 4) umma_commit_pair(BAR(kBarPeFree), 3);
         }
       }
@@ -216,8 +233,10 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
         const long long L = it * kNumLayers + l;
         const int buf = (int)(L & 1);
         const uint32_t use = (uint32_t)(L >> 1);
+        if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 0);
         mbar_wait(BAR(kBarAccFull + buf), use & 1u, abort_flag, prm.status, 300 + q);
         tc_fence_after();
+        if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 1);
         const float* bias = prm.bias + l * 512;
         for (int nt = 0; nt < 2; ++nt) {
           const bool small = (l == 8 && nt == 1);
@@ -256,6 +275,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(BAR(kBarAReady + (f0 >> 6)), 0);
+                if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 2 + nt);
               }
             } else if (p < prm.P) {
               // last layer: column 0 = sdf, columns 1..256 = features
@@ -278,6 +298,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(BAR(kBarAccEmpty + buf), 0);
+        if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 4);
       }
     }
   } else if (warp >= 4 + kEpiWarps) {
@@ -334,7 +355,7 @@ DevStatus* g_status = nullptr;  // one device-side status record per process (de
 
 static int launch_tc(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
                      float* out_feat, int64_t P, int passes, int dbg_layer, float* dbg_out, int* status_host,
-                     cudaStream_t st) {
+                     unsigned long long* trace, cudaStream_t st) {
   if (passes != 1 && passes != 3) return RECMV_E_DTYPE;
   PackedLayout L = packed_layout();
   const char* pb = (const char*)packed;
@@ -367,7 +388,7 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   prm.src = src; prm.pw = pw;
   prm.bias = (const float*)(pb + L.bias_all_off);
   prm.out_sdf = out_sdf; prm.out_feat = out_feat; prm.P = P; prm.passes = passes; prm.status = sd;
-  prm.dbg_layer = dbg_layer; prm.dbg_out = dbg_out;
+  prm.dbg_layer = dbg_layer; prm.dbg_out = dbg_out; prm.trace = trace;
   int64_t tiles = (P + 127) / 128;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = (int)tiles;
@@ -386,7 +407,7 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
 
 int tc_sdf_forward(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
                    float* out_feat, int64_t P, int passes, cudaStream_t st) {
-  return launch_tc(src, packed, pw, out_sdf, out_feat, P, passes, -1, nullptr, nullptr, st);
+  return launch_tc(src, packed, pw, out_sdf, out_feat, P, passes, -1, nullptr, nullptr, nullptr, st);
 }
 
 }  // namespace recmv
@@ -397,7 +418,7 @@ using namespace recmv;
 // the device status record (which bounded wait timed out, if any) plus the raw accumulator of one layer.
 extern "C" int recmv_sdf_mlp_tc_debug(const float* x, const void* packed, const float* pe_w, float* out_sdf,
                                       float* out_feat, int64_t P, int passes, int dbg_layer, float* dbg_out,
-                                      int* status_host, recmv_stream_t stream) {
+                                      int* status_host, unsigned long long* trace, recmv_stream_t stream) {
   if (P <= 0) return RECMV_E_SHAPE;
   if (!x || !packed || !pe_w || !out_sdf || !status_host) return RECMV_E_NULL;
   PointSource src = {};
@@ -405,6 +426,6 @@ extern "C" int recmv_sdf_mlp_tc_debug(const float* x, const void* packed, const 
   src.S = 1;
   PeWeights pw;
   for (int i = 0; i < 12; ++i) pw.w[i] = pe_w[i];
-  return launch_tc(src, packed, pw, out_sdf, out_feat, P, passes, dbg_layer, dbg_out, status_host,
+  return launch_tc(src, packed, pw, out_sdf, out_feat, P, passes, dbg_layer, dbg_out, status_host, trace,
                    (cudaStream_t)stream);
 }

@@ -26,7 +26,7 @@ def run_debug(x, packed, P, passes, layer):
     st = (ctypes.c_int * 4)()
     pe = (ctypes.c_float * 12)(*([1.0] * 12))
     rc = lib.recmv_sdf_mlp_tc_debug(x.data_ptr(), packed.data_ptr(), pe, sdf.data_ptr(), feat.data_ptr(), P,
-                                    passes, layer, dbg.data_ptr(), st, None)
+                                    passes, layer, dbg.data_ptr(), st, None, None)
     torch.cuda.synchronize()
     return rc, list(st), sdf, feat, dbg
 
