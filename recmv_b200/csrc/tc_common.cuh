@@ -50,22 +50,27 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on a barrier that lives in CTA `rank` of the cluster (cluster-scope release)
+// Arrive on a barrier that lives in CTA `rank` of the cluster.  Default (release.cta) semantics, as
+// CUTLASS's ClusterBarrier does: the data these barriers guard is consumed through the async proxy
+// (tensor-core operand reads) after a fence.proxy.async by the writer.  The .release.cluster /
+// .acquire.cluster forms compile to MEMBAR + ERRBAR on the arrive and a CCTL.IVALL (L1 invalidate-all,
+// ~700 cycles measured) after EVERY try_wait -- that made the single MMA-issuing thread the bottleneck
+// of the first version of this kernel (profiles/r01_tc_timeline_before.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   uint32_t remote = mapa(bar, rank);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t rank, uint32_t bytes) {
   uint32_t remote = mapa(bar, rank);
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(bytes) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(remote), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
