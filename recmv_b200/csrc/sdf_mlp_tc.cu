@@ -31,6 +31,7 @@ namespace {
 
 constexpr int kThreads = 448;  // 4 role warps + 8 epilogue warps + 2 prologue warps
 constexpr int kEpiWarps = 8;
+constexpr int kPairs = 2;  // MMA pairs per cluster sharing every weight tile through TMA multicast
 constexpr int kRowsPerCta = 64;
 constexpr int kSlots = 5;
 constexpr uint32_t kSlotBytes = 16384;
@@ -42,8 +43,8 @@ constexpr uint32_t kOffPeLo = 139264;
 constexpr uint32_t kOffW = 147456;
 constexpr uint32_t kOffBar = kOffW + kSlots * kSlotBytes;  // 229376
 // barrier indices (8 bytes each)
-constexpr int kBarFull = 0;      // [5] leader: weight slot filled (2 arrivals + tx bytes of both CTAs)
-constexpr int kBarEmpty = 5;     // [5] local : weight slot consumed (tcgen05.commit multicast)
+constexpr int kBarFull = 0;      // [5] pair leader: weight slot filled (1 arming arrival + tx bytes of both CTAs)
+constexpr int kBarEmpty = 5;     // [5] cluster CTAs 0/1: slot consumed by every pair (one tcgen05.commit per pair)
 constexpr int kBarAReady = 10;   // [8] leader: activation K-block written by both CTAs (4 warp arrivals)
 constexpr int kBarPeReady = 18;  //     leader: positional-encoding block written (4 warp arrivals)
 constexpr int kBarPeFree = 19;   //     local : layer-4 MMAs done with the PE block (commit multicast)
@@ -94,9 +95,8 @@ __device__ __forceinline__ float softplus100_fast(float z) {
 
 }  // namespace
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant__ CUtensorMap tmap16,
-              const TcParams prm) {
+__global__ void __cluster_dims__(2 * kPairs, 1, 1) __launch_bounds__(kThreads, 1)
+sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -106,23 +106,32 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
   volatile unsigned char* valid = reinterpret_cast<volatile unsigned char*>(gbase + kOffMisc + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();       // rank in the cluster (0 .. 2*kPairs-1)
+  const uint32_t pair = crank >> 1;               // MMA pair inside the cluster
+  const uint32_t rank = crank & 1u;               // rank inside the pair (0 = leader, issues the MMAs)
+  const uint32_t lrank = crank & ~1u;             // cluster rank of this pair's leader
   const bool leader = rank == 0;
   const long long num_tiles = (prm.P + 127) / 128;
-  const long long cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const long long cluster_id = blockIdx.x / (2 * kPairs), num_clusters = gridDim.x / (2 * kPairs);
+  // every pair of a cluster iterates the same number of times (they consume the multicast weight stream
+  // in lockstep); iterations past the last tile run on zero rows and write nothing
+  const long long n_iter = (num_tiles + (long long)kPairs * num_clusters - 1) / ((long long)kPairs * num_clusters);
+  auto tile_of = [&](long long it) { return (cluster_id + it * num_clusters) * kPairs + (long long)pair; };
   const int passes = prm.passes;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
-    for (int s = 0; s < kSlots; ++s) { mbar_init(BAR(kBarFull + s), 2); mbar_init(BAR(kBarEmpty + s), 1); }
+    for (int s = 0; s < kSlots; ++s) { mbar_init(BAR(kBarFull + s), 1); mbar_init(BAR(kBarEmpty + s), kPairs); }
     for (int k = 0; k < 8; ++k) mbar_init(BAR(kBarAReady + k), 4);
     mbar_init(BAR(kBarPeReady), 4);
     mbar_init(BAR(kBarPeFree), 1);
     for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 1); mbar_init(BAR(kBarAccEmpty + b), 2 * kEpiWarps); }
+    // arm generation 0 of every weight slot of this pair (both CTAs' halves: 2 x 16 KB)
+    if (leader) for (int s = 0; s < kSlots; ++s) mbar_expect_tx_local(BAR(kBarFull + s), 2 * kSlotBytes);
     fence_mbar_init();
   }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tmap128); prefetch_tmap(&tmap16); }
+  if (warp == 0 && lane == 0) prefetch_tmap(&tmap128);
   if (warp == 2) tmem_alloc_pair(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -131,12 +140,13 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================================ TMA producer (both CTAs) ==================================
-    if (lane == 0) {
+    // ============== TMA producer: cluster CTAs 0 and 1 load one half each, multicast to all pairs ==============
+    if (lane == 0 && crank < 2) {
       int slot = 0;
       uint32_t ring = 0;
-      long long it = 0;
-      for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      uint16_t mask = 0;
+      for (int g = 0; g < kPairs; ++g) mask |= (uint16_t)(1u << (2 * g + (int)rank));
+      for (long long it = 0; it < n_iter; ++it) {
         for (int l = 0; l < kNumLayers; ++l) {
           const int nkb = num_panels(l);
           TRACE(3, it, l, 0);
@@ -144,15 +154,11 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
             const int kbi = kb_order(l, i);
             if (i == nkb - 1) TRACE(3, it, l, 1);
             for (int nt = 0; nt < 2; ++nt) {
-              const bool small = (l == 8 && nt == 1);
               for (int plane = 0; plane < (passes == 3 ? 2 : 1); ++plane) {
                 mbar_wait(BAR(kBarEmpty + slot), ring ^ 1u, abort_flag, prm.status, 100 + slot);
-                const uint32_t bytes = small ? 16u * 128u : 128u * 128u;
-                mbar_expect_tx_cluster(BAR(kBarFull + slot), 0, bytes);
-                const int row = (plane * kNumPanels + panel_base(l) + kbi) * 512 +
-                                (small ? 256 + (int)rank * 16 : nt * 256 + (int)rank * 128);
-                tma_load_2d_pair(base + kOffW + slot * kSlotBytes, small ? (const void*)&tmap16 : (const void*)&tmap128,
-                                 mapa(BAR(kBarFull + slot), 0), 0, row);
+                const int row = (plane * kNumPanels + panel_base(l) + kbi) * 512 + nt * 256 + (int)rank * 128;
+                tma_load_2d_pair_mcast(base + kOffW + slot * kSlotBytes, (const void*)&tmap128,
+                                       mapa(BAR(kBarFull + slot), 0), mask, 0, row);
                 if (++slot == kSlots) { slot = 0; ring ^= 1u; }
               }
             }
@@ -165,8 +171,8 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
     if (leader && lane == 0) {
       int slot = 0;
       uint32_t ring = 0;
-      long long it = 0;
-      for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
+      for (long long it = 0; it < n_iter; ++it) {
         for (int l = 0; l < kNumLayers; ++l) {
           const long long L = it * kNumLayers + l;
           const int buf = (int)(L & 1);
@@ -192,6 +198,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
               const uint32_t idesc = small ? idesc_f16(128, 32) : idesc_f16(128, 256);
               const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + nt * 128);
               mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 230 + slot);
+              mbar_expect_tx_local(BAR(kBarFull + slot), 2 * kSlotBytes);  // arm the slot's next generation
               tc_fence_after();
               uint64_t b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
 #pragma unroll
@@ -200,22 +207,23 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_lo + 2 * k, b + 2 * k, idesc, 1u);
               }
-              umma_commit_pair(BAR(kBarEmpty + slot), 3);
+              umma_commit_pair(BAR(kBarEmpty + slot), 3);  // cluster CTAs 0 and 1 (the producers)
               if (++slot == kSlots) { slot = 0; ring ^= 1u; }
               if (passes == 3) {
                 mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 240 + slot);
+                mbar_expect_tx_local(BAR(kBarFull + slot), 2 * kSlotBytes);
                 tc_fence_after();
                 b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, 1u);
-                umma_commit_pair(BAR(kBarEmpty + slot), 3);
+                umma_commit_pair(BAR(kBarEmpty + slot), 3);  // cluster CTAs 0 and 1 (the producers)
                 if (++slot == kSlots) { slot = 0; ring ^= 1u; }
               }
             }
           }
-          umma_commit_pair(BAR(kBarAccFull + buf), 3);
+          umma_commit_pair(BAR(kBarAccFull + buf), pair_mask);
           TRACE(0, it, l, 5);
-          if (l == 4) umma_commit_pair(BAR(kBarPeFree), 3);
+          if (l == 4) umma_commit_pair(BAR(kBarPeFree), pair_mask);
         }
       }
     }
@@ -226,8 +234,8 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
     const int row = (q & 1) * 32 + lane;  // tile row owned by this thread (lanes 64.. mirror rows 0..63)
     const int half = q >> 1;              // which 128-column half of each 256-wide N tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    long long it = 0;
-    for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    for (long long it = 0; it < n_iter; ++it) {
+      const long long tile = tile_of(it);
       const long long p = tile * 128 + (long long)rank * kRowsPerCta + row;
       for (int l = 0; l < kNumLayers; ++l) {
         const long long L = it * kNumLayers + l;
@@ -247,7 +255,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
             tmem_ld32(tmem_base + lane_addr + (uint32_t)(buf * 256 + nt * 128 + c0), r);
             tmem_ld_wait();
             const int f0 = small ? 256 + half * 16 + c0 : nt * 256 + half * 128 + c0;
-            if (prm.dbg_out && prm.dbg_layer == l && tile == 0 && !small) {
+            if (prm.dbg_out && prm.dbg_layer == l && tile == 0 && !small) {  // cluster 0, pair 0
               float* d = prm.dbg_out + ((size_t)rank * kRowsPerCta + row) * 512 + f0;
 #pragma unroll
               for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(r[c]) * kAccUnscale;
@@ -274,7 +282,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
               if (cc == 32) {  // this warp's 64-wide K block of the next layer's input is complete
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(BAR(kBarAReady + (f0 >> 6)), 0);
+                if (lane == 0) mbar_arrive_cluster(BAR(kBarAReady + (f0 >> 6)), lrank);
                 if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 2 + nt);
               }
             } else if (p < prm.P) {
@@ -297,15 +305,15 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(BAR(kBarAccEmpty + buf), 0);
+        if (lane == 0) mbar_arrive_cluster(BAR(kBarAccEmpty + buf), lrank);
         if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 4);
       }
     }
   } else if (warp >= 4 + kEpiWarps) {
     // ================================ prologue for the next tile (both CTAs) ========================
     const int row = (warp - 4 - kEpiWarps) * 32 + lane;
-    long long it = 0;
-    for (long long tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    for (long long it = 0; it < n_iter; ++it) {
+      const long long tile = tile_of(it);
       const long long p = tile * 128 + (long long)rank * kRowsPerCta + row;
       float pe[40];
       bool ok = true;
@@ -333,7 +341,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
       valid[(it & 1) * 64 + row] = ok ? 1 : 0;
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(BAR(kBarPeReady), 0);
+      if (lane == 0) mbar_arrive_cluster(BAR(kBarPeReady), lrank);
     }
   }
 
@@ -348,7 +356,8 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const __grid_constant
 namespace {
 struct TmapCache {
   const void* base = nullptr;
-  CUtensorMap m128, m16;
+  CUtensorMap m128;
+  int max_clusters = 0;
 };
 DevStatus* g_status = nullptr;  // one device-side status record per process (device 0..n share: reset per launch)
 }  // namespace
@@ -366,8 +375,6 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   const void* panels = pb + L.f16_off;
   if (tc_.base != panels) {
     int s = make_panel_tmap(&tc_.m128, panels, (uint64_t)2 * kNumPanels * 512, 128);
-    if (s) return s;
-    s = make_panel_tmap(&tc_.m16, panels, (uint64_t)2 * kNumPanels * 512, 16);
     if (s) return s;
     tc_.base = panels;
   }
@@ -389,10 +396,26 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   prm.bias = (const float*)(pb + L.bias_all_off);
   prm.out_sdf = out_sdf; prm.out_feat = out_feat; prm.P = P; prm.passes = passes; prm.status = sd;
   prm.dbg_layer = dbg_layer; prm.dbg_out = dbg_out; prm.trace = trace;
+  if (tc_.max_clusters == 0) {
+    // clusters must fit inside a GPC: ask the driver how many 4-CTA clusters are co-resident and run
+    // exactly that many (persistent kernel; a second wave would double the time)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms() / (2 * kPairs) * (2 * kPairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2 * kPairs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sdf_tc_kernel, &cfg);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / (2 * kPairs) - 4; }
+    tc_.max_clusters = n;
+  }
   int64_t tiles = (P + 127) / 128;
-  int clusters = num_sms() / 2;
-  if (tiles < clusters) clusters = (int)tiles;
-  sdf_tc_kernel<<<clusters * 2, kThreads, kSmemBytes, st>>>(tc_.m128, tc_.m16, prm);
+  int64_t want = (tiles + kPairs - 1) / kPairs;
+  int clusters = (int)(want < tc_.max_clusters ? want : tc_.max_clusters);
+  sdf_tc_kernel<<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
   int s = launch_status();
   if (s) return s;
   if (status_host) {  // diagnostics path: synchronous read-back of the device status

@@ -111,6 +111,20 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* 
       ::"r"(smem_dst), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
 
+// Multicast variant: the tile lands at the same smem offset of every CTA in `mask`; with cta_group::2
+// the completion bytes of each destination are signalled on the barrier (same offset) of the leader of
+// that destination's CTA pair.
+__device__ __forceinline__ void tma_load_2d_pair_mcast(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr,
+                                                       uint16_t mask, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar_cluster_addr), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_local(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
@@ -171,16 +185,21 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
   return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
-// fp32 -> fp16 hi/lo split of 8 consecutive K values, packed for one 16-byte store each
+// fp32 -> fp16 hi/lo split of 8 consecutive K values, packed for one 16-byte store each.
+// cvt.rn.f16x2.f32 packs two conversions into one ALU-pipe instruction (F2FP.PACK_AB); the scalar
+// __float2half_rn path compiles to F2F on the quarter-rate XU pipe, which made the epilogue XU-bound.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
 __device__ __forceinline__ void split8(const float v[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-    __half l0 = __float2half_rn(v[2 * i] - __half2float(h0));
-    __half l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
-    h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    h[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+    const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+    l[i] = pack_f16x2(v[2 * i] - back.x, v[2 * i + 1] - back.y);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
