@@ -31,7 +31,10 @@ namespace {
 
 constexpr int kThreads = 448;  // 4 role warps + 8 epilogue warps + 2 prologue warps
 constexpr int kEpiWarps = 8;
-constexpr int kPairs = 2;  // MMA pairs per cluster sharing every weight tile through TMA multicast
+constexpr int kPairs = 1;  // MMA pairs per cluster sharing every weight tile through TMA multicast.
+                           // 2 was measured (profiles/r01_notes.md): correct, halves L2->SM weight traffic, but no
+                           // faster (the MMA phase is bound by the pair's operand path, not by L2) and clusters of 4
+                           // only fit on 132 of the 148 SMs.
 constexpr int kRowsPerCta = 64;
 constexpr int kSlots = 5;
 constexpr uint32_t kSlotBytes = 16384;
@@ -45,7 +48,7 @@ constexpr uint32_t kOffBar = kOffW + kSlots * kSlotBytes;  // 229376
 // barrier indices (8 bytes each)
 constexpr int kBarFull = 0;      // [5] pair leader: weight slot filled (1 arming arrival + tx bytes of both CTAs)
 constexpr int kBarEmpty = 5;     // [5] cluster CTAs 0/1: slot consumed by every pair (one tcgen05.commit per pair)
-constexpr int kBarAReady = 10;   // [8] leader: activation K-block written by both CTAs (4 warp arrivals)
+constexpr int kBarAReady = 10;   // [8] leader: activation K-block written by both CTAs (8 warp arrivals)
 constexpr int kBarPeReady = 18;  //     leader: positional-encoding block written (4 warp arrivals)
 constexpr int kBarPeFree = 19;   //     local : layer-4 MMAs done with the PE block (commit multicast)
 constexpr int kBarAccFull = 20;  // [2] local : layer accumulator complete (commit multicast)
@@ -76,12 +79,16 @@ struct TcParams {
       prm.trace[((((role) * 2 + (it)) * 9 + (l)) << 4) + (ev)] = (unsigned long long)clock64();     \
   } while (0)
 
-// K-block processing order of a layer's input: the 8 epilogue warps release K blocks 0-3 (first N tile)
-// then 4-7 together; the skip layer starts with the PE block, which is ready long before.
+// K-block processing order of a layer's input.  The two warps of a TMEM quadrant split every 64-column
+// K block in two 32-column halves, so the epilogue releases K blocks {0,2} (lane halves 0/1 of the first
+// N tile), then {1,3}, then {4,6}, {5,7}; the skip layer starts with the PE block, ready long before.
 __device__ __forceinline__ int kb_order(int l, int i) {
   if (l == 0) return 0;
-  if (l == 4) return i == 0 ? 8 : i - 1;
-  return i;
+  if (l == 4) {
+    if (i == 0) return 8;
+    --i;
+  }
+  return (i & 4) | ((i & 1) << 1) | ((i >> 1) & 1);  // 0,2,1,3,4,6,5,7
 }
 
 // softplus(beta=100, threshold=20) on the MUFU pipe: ex2.approx / lg2.approx (2^-21-grade), 8-way ILP at
@@ -123,7 +130,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   if (threadIdx.x == 0) {
     *abort_flag = 0;
     for (int s = 0; s < kSlots; ++s) { mbar_init(BAR(kBarFull + s), 1); mbar_init(BAR(kBarEmpty + s), kPairs); }
-    for (int k = 0; k < 8; ++k) mbar_init(BAR(kBarAReady + k), 4);
+    for (int k = 0; k < 8; ++k) mbar_init(BAR(kBarAReady + k), 8);
     mbar_init(BAR(kBarPeReady), 4);
     mbar_init(BAR(kBarPeFree), 1);
     for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 1); mbar_init(BAR(kBarAccEmpty + b), 2 * kEpiWarps); }
@@ -230,7 +237,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ================================ epilogue (both CTAs) =========================================
     const int q = warp & 3;               // TMEM lane quadrant == warp index % 4
-    const int grp = (warp - 4) >> 2;      // which 64-column K block of this quadrant's 128-column half
+    const int grp = (warp - 4) >> 2;      // which 32-column half of every K block of this quadrant
     const int row = (q & 1) * 32 + lane;  // tile row owned by this thread (lanes 64.. mirror rows 0..63)
     const int half = q >> 1;              // which 128-column half of each 256-wide N tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -250,7 +257,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           const bool small = (l == 8 && nt == 1);
           if (small && grp != 0) continue;  // the 32-wide tail tile has a single 16-column group per half
           for (int cc = 0; cc < (small ? 32 : 64); cc += 32) {
-            const int c0 = small ? cc : grp * 64 + cc;
+            const int c0 = small ? cc : cc * 2 + grp * 32;  // K block (cc/32) of this half, 32-column part grp
             uint32_t r[32];
             tmem_ld32(tmem_base + lane_addr + (uint32_t)(buf * 256 + nt * 128 + c0), r);
             tmem_ld_wait();
@@ -279,7 +286,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                 st_shared_v4(base + kOffAHi + off, hi);
                 st_shared_v4(base + kOffALo + off, lo);
               }
-              if (cc == 32) {  // this warp's 64-wide K block of the next layer's input is complete
+              {  // this warp's 32 columns of K block (f0 >> 6) of the next layer's input are complete
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(BAR(kBarAReady + (f0 >> 6)), lrank);
