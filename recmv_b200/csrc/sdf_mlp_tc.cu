@@ -157,16 +157,22 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         for (int l = 0; l < kNumLayers; ++l) {
           const int nkb = num_panels(l);
           TRACE(3, it, l, 0);
-          for (int i = 0; i < nkb; ++i) {
-            const int kbi = kb_order(l, i);
-            if (i == nkb - 1) TRACE(3, it, l, 1);
-            for (int nt = 0; nt < 2; ++nt) {
-              for (int plane = 0; plane < (passes == 3 ? 2 : 1); ++plane) {
-                mbar_wait(BAR(kBarEmpty + slot), ring ^ 1u, abort_flag, prm.status, 100 + slot);
-                const int row = (plane * kNumPanels + panel_base(l) + kbi) * 512 + nt * 256 + (int)rank * 128;
-                tma_load_2d_pair_mcast(base + kOffW + slot * kSlotBytes, (const void*)&tmap128,
-                                       mapa(BAR(kBarFull + slot), 0), mask, 0, row);
-                if (++slot == kSlots) { slot = 0; ring ^= 1u; }
+          // last layer, parity mode: sweep 0 streams (w_hi, w_lo) for the correction MMAs, sweep 1 streams
+          // w_hi again for the hi*hi MMAs (see the MMA issuer)
+          const int nsweep = (passes == 3 && l == kNumLayers - 1) ? 2 : 1;
+          for (int sweep = 0; sweep < nsweep; ++sweep) {
+            for (int i = 0; i < nkb; ++i) {
+              const int kbi = kb_order(l, i);
+              if (i == nkb - 1) TRACE(3, it, l, 1);
+              for (int nt = 0; nt < 2; ++nt) {
+                const int nplanes = (passes == 3 && sweep == 0) ? 2 : 1;
+                for (int plane = 0; plane < nplanes; ++plane) {
+                  mbar_wait(BAR(kBarEmpty + slot), ring ^ 1u, abort_flag, prm.status, 100 + slot);
+                  const int row = (plane * kNumPanels + panel_base(l) + kbi) * 512 + nt * 256 + (int)rank * 128;
+                  tma_load_2d_pair_mcast(base + kOffW + slot * kSlotBytes, (const void*)&tmap128,
+                                         mapa(BAR(kBarFull + slot), 0), mask, 0, row);
+                  if (++slot == kSlots) { slot = 0; ring ^= 1u; }
+                }
               }
             }
           }
@@ -189,42 +195,62 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           tc_fence_after();
           TRACE(0, it, l, 1);
           const int nkb = num_panels(l);
-          for (int i = 0; i < nkb; ++i) {
-            const int kbi = kb_order(l, i);
-            const bool is_pe = (l == 0) || (l == 4 && kbi == 8);
-            if (l == 0) mbar_wait(BAR(kBarPeReady), (uint32_t)(it & 1), abort_flag, prm.status, 210);
-            if (!is_pe) mbar_wait(BAR(kBarAReady + kbi), (uint32_t)((l - 1) & 1), abort_flag, prm.status, 220 + kbi);
-            tc_fence_after();
-            if (i == 0) TRACE(0, it, l, 2);
-            if (i == 4) TRACE(0, it, l, 3);
-            if (i == nkb - 1) TRACE(0, it, l, 4);
-            const uint64_t a_hi = smem_desc_sw128(is_pe ? base + kOffPeHi : base + kOffAHi + kbi * 8192);
-            const uint64_t a_lo = smem_desc_sw128(is_pe ? base + kOffPeLo : base + kOffALo + kbi * 8192);
-            for (int nt = 0; nt < 2; ++nt) {
-              const bool small = (l == 8 && nt == 1);
-              const uint32_t idesc = small ? idesc_f16(128, 32) : idesc_f16(128, 256);
-              const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + nt * 128);
-              mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 230 + slot);
-              mbar_expect_tx_local(BAR(kBarFull + slot), 2 * kSlotBytes);  // arm the slot's next generation
-              tc_fence_after();
-              uint64_t b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-              if (passes == 3) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_lo + 2 * k, b + 2 * k, idesc, 1u);
-              }
-              umma_commit_pair(BAR(kBarEmpty + slot), 3);  // cluster CTAs 0 and 1 (the producers)
-              if (++slot == kSlots) { slot = 0; ring ^= 1u; }
-              if (passes == 3) {
-                mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 240 + slot);
-                mbar_expect_tx_local(BAR(kBarFull + slot), 2 * kSlotBytes);
+          // Ordering for accuracy (parity mode, last layer): the tensor core accumulates with truncation, so
+          // every MMA added to a LARGE accumulator costs ~1 ulp of it.  The correction products (lo*hi,
+          // hi*lo) are 2^-11 of the result: issued first, while the accumulator is still tiny, their
+          // truncations are negligible; the 32 hi*hi MMAs follow in a second sweep over the K blocks
+          // (96 -> 32 significant truncations).  Other layers keep one sweep (w_hi is streamed once).
+          const bool two_sweeps = (passes == 3 && l == kNumLayers - 1);
+          for (int sweep = 0; sweep < (two_sweeps ? 2 : 1); ++sweep) {
+            for (int i = 0; i < nkb; ++i) {
+              const int kbi = kb_order(l, i);
+              const bool is_pe = (l == 0) || (l == 4 && kbi == 8);
+              if (sweep == 0) {
+                if (l == 0) mbar_wait(BAR(kBarPeReady), (uint32_t)(it & 1), abort_flag, prm.status, 210);
+                if (!is_pe) mbar_wait(BAR(kBarAReady + kbi), (uint32_t)((l - 1) & 1), abort_flag, prm.status, 220 + kbi);
                 tc_fence_after();
-                b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
+                if (i == 0) TRACE(0, it, l, 2);
+                if (i == 4) TRACE(0, it, l, 3);
+                if (i == nkb - 1) TRACE(0, it, l, 4);
+              }
+              const uint64_t a_hi = smem_desc_sw128(is_pe ? base + kOffPeHi : base + kOffAHi + kbi * 8192);
+              const uint64_t a_lo = smem_desc_sw128(is_pe ? base + kOffPeLo : base + kOffALo + kbi * 8192);
+              for (int nt = 0; nt < 2; ++nt) {
+                const bool small = (l == 8 && nt == 1);
+                const uint32_t idesc = small ? idesc_f16(128, 32) : idesc_f16(128, 256);
+                const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + nt * 128);
+                // ---- slot with w_hi -------------------------------------------------------------------
+                mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 230 + slot);
+                mbar_expect_tx_local(BAR(kBarFull + slot), 2 * kSlotBytes);  // arm the slot's next generation
+                tc_fence_after();
+                uint64_t b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
+                if (!two_sweeps) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, 1u);
+                  for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                  if (passes == 3) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_lo + 2 * k, b + 2 * k, idesc, 1u);
+                  }
+                } else if (sweep == 0) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_lo + 2 * k, b + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, 1u);
+                }
                 umma_commit_pair(BAR(kBarEmpty + slot), 3);  // cluster CTAs 0 and 1 (the producers)
                 if (++slot == kSlots) { slot = 0; ring ^= 1u; }
+                // ---- slot with w_lo (parity mode; not in the hi*hi sweep) -----------------------------------
+                if (passes == 3 && sweep == 0) {
+                  mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 240 + slot);
+                  mbar_expect_tx_local(BAR(kBarFull + slot), 2 * kSlotBytes);
+                  tc_fence_after();
+                  b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, 1u);
+                  umma_commit_pair(BAR(kBarEmpty + slot), 3);
+                  if (++slot == kSlots) { slot = 0; ring ^= 1u; }
+                }
               }
             }
           }
