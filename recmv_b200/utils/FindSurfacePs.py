@@ -1,0 +1,97 @@
+"""Surface-point seeding and the Newton-like surface/ray root solve -- API of utils/FindSurfacePs.py
+(:7-60 FindSurfacePs, :145-207 OptimizeSurfacePs, :210-272 OptimizeGarmentSurfaceSinlge, :273-353
+OptimizeGarmentSurfacePs).
+
+The three Optimize* functions of the reference are one algorithm copied three times; here they share
+`_solve`.  Per iteration on the not-yet-converged subset:
+    L = w1 |f(p)| + w2 |(D(p)-c) x v| / |D(p)-c| ,  g = dL/dp ,  p <- p - L g / |g|^2
+converged when |f| < dthreshold and asin(|(D-c) x v| / |D-c|) * 180/pi < athreshold.
+All no-grad evaluations (the convergence checks) run the fused kernels (one launch for the SDF, one for
+the skinning); the gradient step goes through the autograd path of the same modules.
+"""
+import numpy as np
+import torch
+
+
+def FindSurfacePs(TmpVs, TmpFaces, frags):
+    """Rasteriser fragments -> (batch, row, col) of covered pixels, barycentric seed points on the canonical
+    mesh and the face ids (utils/FindSurfacePs.py:7-60).  frags: .pix_to_face [N,H,W,K] i64,
+    .bary_coords [N,H,W,K,3]."""
+    pix_to_face = frags.pix_to_face
+    bary = frags.bary_coords
+    N, H, W, K = pix_to_face.shape
+    inner = (bary > 0.0).all(-1) & (pix_to_face >= 0)                # [N,H,W,K]
+    # first valid k per pixel (the reference takes a scatter-min over the nonzero columns, :26-30)
+    first = torch.where(inner, torch.arange(K, device=inner.device).view(1, 1, 1, K),
+                        torch.full((1, 1, 1, 1), K, device=inner.device)).min(dim=-1).values
+    covered = inner.any(dim=-1)
+    batch_inds, row_inds, col_inds = covered.nonzero(as_tuple=True)
+    k = first[covered].view(-1, 1)
+    finds = torch.gather(pix_to_face[covered], 1, k).view(-1)
+    finds = finds % TmpFaces.shape[0]                                # packed -> per-mesh face index
+    ws = torch.gather(bary[covered], 1, k.view(-1, 1, 1).expand(-1, 1, 3)).view(-1, 3)
+    initTmpPs = (TmpVs[TmpFaces[finds].view(-1)].view(-1, 3, 3) * ws[:, :, None]).sum(1)
+    return batch_inds, row_inds, col_inds, initTmpPs, finds
+
+
+def _angle_ok(direct, rays, athreshold):
+    up = torch.cross(direct, rays, dim=1)
+    return torch.arcsin(up.norm(dim=1) / direct.norm(dim=1)) * 180. / np.pi < athreshold
+
+
+def _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2,
+           times):
+    """deform(ps, inds) -> posed points.  Mutates and returns initTmpPs like the reference."""
+    cam = cam_pos.view(1, 3)
+    with torch.no_grad():
+        check = (tmpSdf(initTmpPs, ratio).view(-1).abs() < dthreshold) & \
+            _angle_ok(deform(initTmpPs, batch_inds) - cam, rays, athreshold)
+        unfinished = ~check
+    for _ in range(times):
+        sel = unfinished.nonzero(as_tuple=False).view(-1)   # one sync per iteration (reference: several)
+        if sel.numel() == 0:
+            break
+        cur = initTmpPs[sel].detach().clone().requires_grad_(True)
+        loss1 = tmpSdf(cur, ratio).abs().view(-1)
+        direct = deform(cur, batch_inds[sel]) - cam
+        up = torch.cross(direct, rays[sel], dim=1)
+        loss2 = (up.norm(dim=1) / direct.norm(dim=1)).abs()
+        loss = w1 * loss1 + w2 * loss2
+        grad = torch.autograd.grad(loss.sum(), cur, retain_graph=False, create_graph=False, only_inputs=True)[0]
+        t = -loss / (grad * grad).sum(1)
+        cur = (cur + t.view(-1, 1) * grad).detach()
+        initTmpPs[sel] = cur
+        with torch.no_grad():
+            ok = (tmpSdf(cur, ratio).view(-1).abs() < dthreshold) & \
+                _angle_ok(deform(cur, batch_inds[sel]) - cam, rays[sel], athreshold)
+            unfinished[sel[ok]] = False
+    return initTmpPs.detach(), ~unfinished
+
+
+def OptimizeSurfacePs(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deformer, defconds,
+                      dthreshold=5.e-5, athreshold=0.02, w1=3.05, w2=1., times=5):
+    def deform(ps, inds):
+        return deformer(ps, defconds, inds, ratio=ratio)
+    return _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2, times)
+
+
+def OptimizeGarmentSurfaceSinlge(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deformer, defconds,
+                                 dthreshold=5.e-5, athreshold=0.02, w1=3.05, w2=1., times=5, offset_type=None):
+    def deform(ps, inds):
+        return deformer(ps, defconds, inds, ratio=ratio, offset_type=offset_type)
+    return _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2, times)
+
+
+def OptimizeGarmentSurfacePs(cam_pos, rays_list, initTmpPs_list, batch_inds_list, tmpSdf_nets, ratio, deformer,
+                             defconds_list, garment_names, dthreshold=5.e-5, athreshold=0.02, w1=3.05, w2=1.,
+                             times=5):
+    smpl_conds = defconds_list[1]
+    out_ps, out_ok = [], []
+    for gi, (ps, inds, dcond, rays, name) in enumerate(zip(initTmpPs_list, batch_inds_list, defconds_list[0],
+                                                            rays_list, garment_names)):
+        def deform(p, i, dcond=dcond, name=name):
+            return deformer(p, [dcond, smpl_conds], i, ratio=ratio, offset_type=name)
+        p, ok = _solve(cam_pos, rays, ps, inds, tmpSdf_nets[gi], ratio, deform, dthreshold, athreshold, w1, w2, times)
+        out_ps.append(p)
+        out_ok.append(ok)
+    return out_ps, out_ok

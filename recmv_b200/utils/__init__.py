@@ -1,0 +1,68 @@
+"""Mirror of the hot-path helpers of the reference's `utils` package (utils/utils.py:8-18,40-46,133-156,
+198-264).  Same names, arguments and return values; the native calls go to librecmv_b200.so."""
+import torch
+
+from ..model.Embedder import annealing_weights  # noqa: F401  (utils/utils.py:40-46)
+from ..ops import FastDiff3x3MinvFunction  # noqa: F401    (utils/utils.py:8-18)
+from . import FindSurfacePs as _fsp
+from .FindSurfacePs import (FindSurfacePs, OptimizeGarmentSurfacePs, OptimizeGarmentSurfaceSinlge,  # noqa: F401
+                            OptimizeSurfacePs)
+
+
+def compute_Jacobian(ps, ds, retain_graph, create_graph, allow_unused=False):
+    """J = dD/dp by three autograd passes (utils/utils.py:133-156) -> [N,3,3], row i = grad of D_i."""
+    rows = []
+    go = torch.ones_like(ds[..., 0])
+    for i in range(3):
+        keep = True if i < 2 else retain_graph
+        g = torch.autograd.grad(ds[..., i], ps, go, retain_graph=keep, create_graph=create_graph,
+                                allow_unused=allow_unused)
+        rows.append(g[0].view(-1, 1, 3))
+    return torch.cat(rows, dim=1)
+
+
+def _deform(deformer, ps, defconds, batch_inds, ratio, offset_type):
+    return deformer(ps, defconds, batch_inds, ratio=ratio, offset_type=offset_type)
+
+
+def compute_cardinal_rays(deformer, ps, rays, defconds, batch_inds, ratio, phase, offset_type=None):
+    """crays = normalize(J^-1 v) with the FastMinv singularity fallback (utils/utils.py:232-250)."""
+    check = phase in ('train', 'Train')
+    ds = _deform(deformer, ps, defconds, batch_inds, ratio, offset_type)
+    J = compute_Jacobian(ps, ds, check, check)
+    Jinv, ok = FastDiff3x3MinvFunction.apply(J)
+    crays = Jinv.matmul(rays.view(-1, 3, 1)).view(-1, 3)
+    bad = ~ok
+    if bad.sum().item() > 0:
+        print('unwished error n_inv_mask:(%d:%d)' % (bad.sum().item(), bad.numel()))
+        fixed = torch.zeros_like(crays)
+        fixed[ok] = crays[ok]
+        fixed[bad] = rays[bad].detach()
+        crays = fixed
+    crays = crays / crays.norm(dim=1, keepdim=True)
+    return crays, ds
+
+
+def compute_deformed_normals(sdf, deformer, ps, defconds, batch_inds, ratio, phase, offset_type):
+    """n = normalize(J^-T grad sdf) (utils/utils.py:198-230)."""
+    sdfs = sdf(ps, ratio)
+    check = phase in ('train', 'Train')
+    onx = torch.autograd.grad(sdfs, ps, torch.ones_like(sdfs), retain_graph=check, create_graph=check)[0]
+    ds = _deform(deformer, ps, defconds, batch_inds, ratio, offset_type)
+    J = compute_Jacobian(ps, ds, check, check)
+    Jinv, ok = FastDiff3x3MinvFunction.apply(J)
+    nx = Jinv.transpose(-2, -1).matmul(onx.view(-1, 3, 1)).view(-1, 3)
+    bad = ~ok
+    if bad.sum().item() > 0:
+        print('unwished error n_inv_mask:(%d:%d)' % (bad.sum().item(), bad.numel()))
+        fixed = torch.zeros_like(nx)
+        fixed[ok] = nx[ok]
+        fixed[bad] = J[bad].matmul(onx[bad].unsqueeze(-1)).view(-1, 3)
+        nx = fixed
+    nx = nx / nx.norm(dim=1, keepdim=True)
+    return nx, ds
+
+
+def compute_netRender_color(net, ps, ds, ns, vs, features, framefeatures, ratio):
+    """utils/utils.py:252-264 (the per-frame condition is ignored by the reference as well)."""
+    return net(ps, ns, vs, features, ratio)

@@ -120,6 +120,90 @@ def main():
     save("gridsample.npz", input=inp, grid=grid, out=ref, grad_out=go, grad_input=gi.detach(),
          grad_grid=ggr.detach(), gg_input=ggi, gg_grid=ggg, d_input=d0, d_grid=d1, d_gout=d2)
 
+    surface_goldens(ns)
+
+
+class Frags:
+    def __init__(self, pix_to_face, bary_coords):
+        self.pix_to_face, self.bary_coords = pix_to_face, bary_coords
+
+
+def surface_scene(mod_net, mod_def, device="cpu"):
+    """Shared by the generator (reference classes) and the GPU tests (this package's classes)."""
+    sdf = testing.build_sdf(mod_net.getTmpSdf, seed=0, perturb_seed=101, device=device)
+    torch.manual_seed(1)
+    tr = mod_def.MLPTranslator(128, 6)
+    testing.perturb_module(tr, 202, scale=0.5)
+    Js, parents, init = synth.skeleton()
+    ws = synth.skinning_voxel((17, 33, 21), seed=7)
+    sk = mod_def.LBSkinner(ws, [-1.1] * 3, [1.1] * 3, Js, parents, init_pose=init,
+                           bbox_extend=torch.tensor(synth.BBOX_EXTEND), bbox_center=torch.tensor(synth.BBOX_CENTER))
+    deformer = mod_def.CompositeDeformer([tr, sk]).to(device)
+    return sdf, deformer
+
+
+def surface_inputs(sdf, deformer):
+    """Seeds as the real pipeline produces them: points ON the zero level set (bisection along a radial
+    line), rays through their deformed positions, then a 2e-3 perturbation (marching-cubes / rasteriser
+    discretisation error) -- the solve only has to polish."""
+    g = synth.generator(4242)
+    n = 600
+    dirs = torch.nn.functional.normalize(torch.randn((n, 3), generator=g), dim=1)
+    poses, trans = synth.poses_trans(2, seed=11)
+    conds = torch.randn((2, 128), generator=g) * 0.1
+    binds = torch.randint(0, 2, (n,), generator=g)
+    cam = torch.tensor(synth.CAM_POS)
+    ratio = {"sdfRatio": 0.8, "deformerRatio": 0.6, "renderRatio": 0.9}
+    lo, hi = torch.full((n, 1), 0.3), torch.full((n, 1), 0.9)
+    with torch.no_grad():
+        for _ in range(40):
+            mid = 0.5 * (lo + hi)
+            neg = sdf(dirs * mid, ratio) < 0
+            lo, hi = torch.where(neg, mid, lo), torch.where(neg, hi, mid)
+        ps_true = dirs * (0.5 * (lo + hi))
+        d0 = deformer(ps_true, [conds, [poses, trans]], binds, ratio=ratio, offset_type="body")
+    rays = torch.nn.functional.normalize(d0 - cam.view(1, 3), dim=1)
+    seeds = ps_true + torch.randn((n, 3), generator=g) * 2e-3
+    return ps_true, seeds, rays, poses, trans, conds, binds, cam, ratio
+
+
+def surface_goldens(ns):
+    sdf, deformer = surface_scene(ns.network, ns.Deformer)
+    p0, seeds, rays, poses, trans, conds, binds, cam, ratio = surface_inputs(sdf, deformer)
+    defconds = [conds, [poses, trans]]
+    fsp = ns.FindSurfacePs
+    ps, ok = fsp.OptimizeGarmentSurfaceSinlge(cam, rays, seeds.clone(), binds, sdf, ratio, deformer, defconds,
+                                              dthreshold=1.e-4, athreshold=0.05, w1=3.05, w2=1., times=10,
+                                              offset_type="body")
+    ps1, ok1 = fsp.OptimizeSurfacePs(cam, rays, seeds.clone(), binds, sdf, ratio,
+                                     lambda p, c, i, **kw: deformer(p, c, i, ratio=kw["ratio"], offset_type="body"),
+                                     defconds, dthreshold=1.e-4, athreshold=0.05, times=1)
+    # cardinal rays / deformed normals at the solved points (test phase: first order only)
+    uu = ns.utils_utils
+    pts = ps.detach().clone().requires_grad_(True)
+    crays, ds = uu.compute_cardinal_rays(deformer, pts, rays, defconds, binds, ratio, "test", offset_type="body")
+    pts2 = ps.detach().clone().requires_grad_(True)
+    nrm, ds2 = uu.compute_deformed_normals(sdf, deformer, pts2, defconds, binds, ratio, "test", "body")
+    with torch.no_grad():
+        sdf_at = sdf(ps, ratio)
+    save("surface.npz", ps_true=p0, seeds=seeds, rays=rays, poses=poses, trans=trans, conds=conds, batch_inds=binds,
+         ps=ps, ok=ok, ps_1it=ps1, ok_1it=ok1, crays=crays.detach(), ds=ds.detach(),
+         normals=nrm.detach(), sdf_at=sdf_at[:, 0])
+    print("surface solve: converged", int(ok.sum()), "of", ok.numel(), "| after 1 it:", int(ok1.sum()))
+
+    # FindSurfacePs on synthetic fragments (K = 2 so the first-valid-k logic is exercised)
+    g = synth.generator(99)
+    V, Fc, N, H, W, K = 50, 80, 2, 12, 10, 2
+    verts = torch.randn((V, 3), generator=g)
+    faces = torch.randint(0, V, (Fc, 3), generator=g)
+    p2f = torch.randint(-1, N * Fc, (N, H, W, K), generator=g)
+    p2f[torch.rand((N, H, W, K), generator=g) < 0.4] = -1
+    bary = torch.rand((N, H, W, K, 3), generator=g)
+    bary[torch.rand((N, H, W, K), generator=g) < 0.2] *= -1.0
+    b, r, c, pts0, fi = fsp.FindSurfacePs(verts, faces, Frags(p2f, bary))
+    save("findsurface.npz", verts=verts, faces=faces, pix_to_face=p2f, bary=bary, batch=b, row=r, col=c, pts=pts0,
+         finds=fi)
+
 
 if __name__ == "__main__":
     main()

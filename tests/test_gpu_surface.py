@@ -1,0 +1,98 @@
+"""GPU: the callers either side of the fused kernels -- Newton-like surface solve (A10), cardinal rays and
+deformed normals (A7), coarse-to-fine sweep + marching cubes (A11/A13) -- against goldens produced by the
+reference's own functions on its own modules (tests/golden/make_golden.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden, norm_err
+sys.path.insert(0, GOLDEN)
+import make_golden as mg  # noqa: E402  (scene builders shared with the generator)
+from recmv_b200 import _lib, ops, synth  # noqa: E402
+from recmv_b200 import model as M  # noqa: E402
+from recmv_b200 import utils as U  # noqa: E402
+from recmv_b200.MCAcc import Seg3dLossless  # noqa: E402
+from recmv_b200.discretize import discretize_sdf  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class _Mods:  # the scene builder expects module namespaces
+    getTmpSdf = staticmethod(M.getTmpSdf)
+    MLPTranslator, LBSkinner, CompositeDeformer = M.MLPTranslator, M.LBSkinner, M.CompositeDeformer
+
+
+def _scene():
+    sdf, deformer = mg.surface_scene(_Mods, _Mods, device="cpu")
+    return sdf.to(DEV), deformer.to(DEV)
+
+
+RATIO = {"sdfRatio": 0.8, "deformerRatio": 0.6, "renderRatio": 0.9}
+
+
+@pytest.mark.parametrize("mode,min_agree", [(_lib.MLP_FP32_SIMT, 0.99), (_lib.MLP_TC_F16X3, 0.97)])
+def test_surface_solve_matches_reference(mode, min_agree):
+    g = load_golden("surface.npz")
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in g.items()}
+    sdf, deformer = _scene()
+    sdf.mlp_mode = mode
+    defconds = [t["conds"], [t["poses"], t["trans"]]]
+    cam = torch.tensor(synth.CAM_POS, device=DEV)
+    ps, ok = U.OptimizeGarmentSurfaceSinlge(cam, t["rays"], t["seeds"].clone(), t["batch_inds"], sdf, RATIO,
+                                            deformer, defconds, dthreshold=1.e-4, athreshold=0.05, w1=3.05,
+                                            w2=1., times=10, offset_type="body")
+    agree = (ok == t["ok"]).float().mean().item()
+    both = ok & t["ok"]
+    print(f"mode {mode}: converged {int(ok.sum())} (reference {int(t['ok'].sum())}), flag agreement {agree:.4f}, "
+          f"max |dp| on common {(ps - t['ps'])[both].abs().max().item():.2e}")
+    assert agree >= min_agree
+    assert (ps - t["ps"])[both].abs().max() < 2e-4       # thresholds are 1e-4: same basin, same point
+    # single iteration: deterministic update formula p <- p - L g/|g|^2
+    ps1, ok1 = U.OptimizeSurfacePs(cam, t["rays"], t["seeds"].clone(), t["batch_inds"], sdf, RATIO,
+                                   lambda p, c, i, **kw: deformer(p, c, i, ratio=kw["ratio"], offset_type="body"),
+                                   defconds, dthreshold=1.e-4, athreshold=0.05, times=1)
+    assert (ok1 == t["ok_1it"]).float().mean() >= min_agree
+    assert (ps1 - t["ps_1it"]).abs().max() < 5e-5
+
+
+def test_cardinal_rays_and_normals_match_reference():
+    g = load_golden("surface.npz")
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in g.items()}
+    sdf, deformer = _scene()
+    defconds = [t["conds"], [t["poses"], t["trans"]]]
+    pts = t["ps"].clone().requires_grad_(True)
+    crays, ds = U.compute_cardinal_rays(deformer, pts, t["rays"], defconds, t["batch_inds"], RATIO, "test", "body")
+    assert norm_err(ds, t["ds"]) < 1e-4 and (crays - t["crays"]).abs().max() < 2e-4
+    pts2 = t["ps"].clone().requires_grad_(True)
+    nrm, _ = U.compute_deformed_normals(sdf, deformer, pts2, defconds, t["batch_inds"], RATIO, "test", "body")
+    assert (nrm - t["normals"]).abs().max() < 2e-4
+    # train phase builds the second-order graph through the CUDA sampler's double backward
+    pts3 = t["ps"][:64].clone().requires_grad_(True)
+    cr, _ = U.compute_cardinal_rays(deformer, pts3, t["rays"][:64], [t["conds"], [t["poses"], t["trans"]]],
+                                    t["batch_inds"][:64], RATIO, "train", "body")
+    cr.pow(2).sum().backward()
+    assert torch.isfinite(pts3.grad).all()
+
+
+def test_c2f_sweep_and_discretize_on_gpu():
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_c2f_cpu import KW, sphere_query
+    eng = Seg3dLossless(sphere_query, **KW).to(DEV)
+    out = eng.forward()
+    gold = torch.from_numpy(np.load(os.path.join(GOLDEN, "c2f_grid.npz"))["grid"]).to(DEV)
+    assert (out[0, 0] - gold).abs().max() < 2e-6 and bool(((out[0, 0] > 0) == (gold > 0)).all())
+    # network as query function: fused launches, watertight mesh close to the analytic level set
+    sdf = M.getTmpSdf(DEV, 6, 0.6, 256)
+    eng2 = Seg3dLossless(None, b_min=[-1, -1, -1], b_max=[1, 1, 1], resolutions=[17, 33, 65, 129],
+                         align_corners=False, balance_value=0.0).to(DEV)
+    v, f = discretize_sdf(sdf, eng2, None)
+    assert sdf.last_path == "fused" and v.shape[0] > 1000 and f.min() >= 0
+    e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).sort(dim=1).values
+    assert bool((torch.unique(e, dim=0, return_counts=True)[1] == 2).all())
+    with torch.no_grad():
+        assert sdf(v, None).abs().max() < 2e-3       # vertices sit on the zero level set (cell size 0.0155)
+    assert sum(s[3] for s in eng2.stats) < 0.25 * 129 ** 3
