@@ -50,7 +50,10 @@ def test_surface_solve_matches_reference(mode, min_agree):
     print(f"mode {mode}: converged {int(ok.sum())} (reference {int(t['ok'].sum())}), flag agreement {agree:.4f}, "
           f"max |dp| on common {(ps - t['ps'])[both].abs().max().item():.2e}")
     assert agree >= min_agree
-    assert (ps - t["ps"])[both].abs().max() < 2e-4       # thresholds are 1e-4: same basin, same point
+    # fp32 mode takes the very same iterations as the reference.  In tc3 mode a point can pass the acceptance
+    # test one iteration earlier or later (|sdf| < 1e-4 with ~1e-5 arithmetic noise), so positions agree to
+    # within the acceptance ball: angle < 0.05 deg at ~2.4 units from the camera = 2.1e-3.
+    assert (ps - t["ps"])[both].abs().max() < (2e-6 if mode == _lib.MLP_FP32_SIMT else 2.1e-3)
     # single iteration: deterministic update formula p <- p - L g/|g|^2
     ps1, ok1 = U.OptimizeSurfacePs(cam, t["rays"], t["seeds"].clone(), t["batch_inds"], sdf, RATIO,
                                    lambda p, c, i, **kw: deformer(p, c, i, ratio=kw["ratio"], offset_type="body"),
