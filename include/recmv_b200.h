@@ -136,6 +136,15 @@ RECMV_API int recmv_sdf_pack_weights(const float* W_all, const float* b_all, voi
 RECMV_API int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float* pe_w /*host*/,
                       float* out_sdf, float* out_feat, int64_t P, int mode, recmv_stream_t stream);
 
+/* ---- A3: sdf and its input gradient (ImplicitNetwork.gradient, model/network.py:121-133; the
+ * autograd.grad(sdf, p) of utils/FindSurfacePs.py:176 and OptimGarmentNetwork.py:1171,3192) --------------
+ * One forward-mode launch of the tcgen05 kernel: every point occupies four tile rows (value and the three
+ * directional derivatives), no activations are stored and no transposed weights are needed.
+ * out_grad [P,3] = d sdf / d x.  TC modes only (RECMV_E_UNSUPPORTED otherwise).                            */
+RECMV_API int recmv_sdf_mlp_fwd_grad(const float* x, const void* packed, const float* pe_w /*host*/,
+                           float* out_sdf, float* out_feat, float* out_grad, int64_t P, int mode,
+                           recmv_stream_t stream);
+
 /* Diagnostics for the tcgen05 path (used by tests/test_gpu_tc_bringup.py): same computation as
  * recmv_sdf_mlp_fwd in a TC mode (passes = 1 or 3), plus status_host[4] = {code, barrier tag, block, 0}
  * of the kernel's bounded mbarrier waits (code 0 = no wait timed out) and, when dbg_out != NULL, the raw

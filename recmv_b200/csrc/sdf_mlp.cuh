@@ -57,4 +57,8 @@ int simt_sdf_forward(const PointSource& src, const void* packed, const PeWeights
 int tc_sdf_forward(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
                    float* out_feat, int64_t P, int passes, cudaStream_t st);
 
+// value + input gradient in one forward-mode launch (tcgen05 path only)
+int tc_sdf_forward_grad(const float* x, const void* packed, const PeWeights& pw, float* out_sdf, float* out_feat,
+                        float* out_grad, int64_t P, int passes, cudaStream_t st);
+
 }  // namespace recmv

@@ -298,6 +298,19 @@ extern "C" int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float
   return run_forward(src, packed, pe_w, out_sdf, out_feat, P, mode, (cudaStream_t)stream);
 }
 
+extern "C" int recmv_sdf_mlp_fwd_grad(const float* x, const void* packed, const float* pe_w, float* out_sdf,
+                                      float* out_feat, float* out_grad, int64_t P, int mode,
+                                      recmv_stream_t stream) {
+  if (P < 0) return RECMV_E_SHAPE;
+  if (P == 0) return RECMV_OK;
+  if (!x || !packed || !pe_w || !out_sdf || !out_grad) return RECMV_E_NULL;
+  if (mode != RECMV_MLP_TC_F16X3 && mode != RECMV_MLP_TC_F16X1) return RECMV_E_UNSUPPORTED;
+  PeWeights pw;
+  for (int i = 0; i < 12; ++i) pw.w[i] = pe_w[i];
+  return tc_sdf_forward_grad(x, packed, pw, out_sdf, out_feat, out_grad, P, mode == RECMV_MLP_TC_F16X3 ? 3 : 1,
+                             (cudaStream_t)stream);
+}
+
 extern "C" int recmv_ray_first_hit(const float* sdf, const recmv_raymarch_t* rm, int32_t* hit_idx,
                                    float* hit_t, int64_t R, recmv_stream_t stream) {
   if (R < 0) return RECMV_E_SHAPE;

@@ -72,6 +72,8 @@ struct TcParams {
   // diagnostics: clock64 stamps of cluster 0 / leader CTA, tiles 0-1: trace[role][it][layer][16]
   // role 0 = MMA thread, 1 = first epilogue warp, 2 = last epilogue warp, 3 = producer
   unsigned long long* trace;
+  // forward-mode (JVP) variant: out_grad [P,3] = d sdf / d x; each point occupies 4 adjacent tile rows
+  float* out_grad;
 };
 #define TRACE(role, it, l, ev)                                                                     \
   do {                                                                                             \
@@ -100,8 +102,20 @@ __device__ __forceinline__ float softplus100_fast(float z) {
   return t > 20.f ? z : y;
 }
 
+// value row: softplus100(z); tangent row: z_tangent * sigmoid(100 z_value)  (d softplus / dz; torch's
+// threshold branch z > 0.2 has derivative 1, which sigmoid(20+) equals to 2e-9)
+__device__ __forceinline__ float act_jvp(float z_own, float z_val, bool is_value) {
+  const float t = 100.f * z_val;
+  const float e = __expf(-fabsf(t));
+  const float inv = __fdividef(1.f, 1.f + e);
+  const float sp = t > 20.f ? z_val : (fmaxf(t, 0.f) + __logf(1.f + e)) * 0.01f;
+  const float sig = t >= 0.f ? inv : e * inv;
+  return is_value ? sp : z_own * sig;
+}
+
 }  // namespace
 
+template <bool kJvp>
 __global__ void __cluster_dims__(2 * kPairs, 1, 1) __launch_bounds__(kThreads, 1)
 sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   extern __shared__ uint8_t smem_raw[];
@@ -118,7 +132,8 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   const uint32_t rank = crank & 1u;               // rank inside the pair (0 = leader, issues the MMAs)
   const uint32_t lrank = crank & ~1u;             // cluster rank of this pair's leader
   const bool leader = rank == 0;
-  const long long num_tiles = (prm.P + 127) / 128;
+  constexpr int kPtsPerTile = kJvp ? 32 : 128;  // JVP: rows = 4 per point (value, d/dx, d/dy, d/dz)
+  const long long num_tiles = (prm.P + kPtsPerTile - 1) / kPtsPerTile;
   const long long cluster_id = blockIdx.x / (2 * kPairs), num_clusters = gridDim.x / (2 * kPairs);
   // every pair of a cluster iterates the same number of times (they consume the multicast weight stream
   // in lockstep); iterations past the last tile run on zero rows and write nothing
@@ -269,7 +284,10 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = tile_of(it);
-      const long long p = tile * 128 + (long long)rank * kRowsPerCta + row;
+      const long long p = kJvp ? tile * 32 + (long long)rank * 16 + (row >> 2)
+                               : tile * 128 + (long long)rank * kRowsPerCta + row;
+      const int comp = kJvp ? (row & 3) : 0;   // 0 = value row, 1..3 = tangent rows
+      const bool is_value = comp == 0;
       for (int l = 0; l < kNumLayers; ++l) {
         const long long L = it * kNumLayers + l;
         const int buf = (int)(L & 1);
@@ -303,8 +321,17 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                               fmaf(__uint_as_float(r[8 * j + 2]), kAccUnscale, b0.z), fmaf(__uint_as_float(r[8 * j + 3]), kAccUnscale, b0.w),
                               fmaf(__uint_as_float(r[8 * j + 4]), kAccUnscale, b1.x), fmaf(__uint_as_float(r[8 * j + 5]), kAccUnscale, b1.y),
                               fmaf(__uint_as_float(r[8 * j + 6]), kAccUnscale, b1.z), fmaf(__uint_as_float(r[8 * j + 7]), kAccUnscale, b1.w)};
+                if (kJvp) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = softplus100_fast(v[e]) * kActScale;
+                  for (int e = 0; e < 8; ++e) {
+                    const float z_own = is_value ? v[e] : __uint_as_float(r[8 * j + e]) * kAccUnscale;  // tangents: no bias
+                    const float z_val = __shfl_sync(0xffffffffu, z_own, lane & ~3);  // the point's value row
+                    v[e] = act_jvp(z_own, z_val, is_value) * kActScale;
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = softplus100_fast(v[e]) * kActScale;
+                }
                 uint4 hi, lo;
                 split8(v, hi, lo);
                 const int kb = f >> 6, chunk = (f & 63) >> 3;
@@ -321,7 +348,9 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
             } else if (p < prm.P) {
               // last layer: column 0 = sdf, columns 1..256 = features
               const bool ok = valid[(it & 1) * 64 + row] != 0;
-              if (!small) {
+              if (kJvp && !is_value) {
+                if (!small && f0 == 0) prm.out_grad[p * 3 + (comp - 1)] = __uint_as_float(r[0]) * kAccUnscale;
+              } else if (!small) {
                 if (f0 == 0) prm.out_sdf[p] = ok ? fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias)) : kInvalidSdf;
                 if (prm.out_feat) {
 #pragma unroll
@@ -347,13 +376,32 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
     const int row = (warp - 4 - kEpiWarps) * 32 + lane;
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = tile_of(it);
-      const long long p = tile * 128 + (long long)rank * kRowsPerCta + row;
+      const long long p = kJvp ? tile * 32 + (long long)rank * 16 + (row >> 2)
+                               : tile * 128 + (long long)rank * kRowsPerCta + row;
       float pe[40];
       bool ok = true;
       if (p < prm.P) {
         float cx, cy, cz;
         ok = fetch_point(prm.src, p, cx, cy, cz);
-        positional_encode(cx, cy, cz, prm.pw.w, pe);
+        if (!kJvp || (row & 3) == 0) {
+          positional_encode(cx, cy, cz, prm.pw.w, pe);
+        } else {
+          // tangent row j: d PE / d x_j  (x -> e_j ; w sin(f x_c) -> w f cos(f x_c) [c == j] ; cos -> -w f sin)
+          const int j = (row & 3) - 1;
+          const float xj = j == 0 ? cx : (j == 1 ? cy : cz);
+#pragma unroll
+          for (int e = 0; e < 39; ++e) pe[e] = 0.f;
+          pe[j] = 1.f;
+          float f = 1.f;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            float sn, cs;
+            sincosf(xj * f, &sn, &cs);
+            pe[3 + 6 * k + j] = prm.pw.w[2 * k] * f * cs;
+            pe[3 + 6 * k + 3 + j] = -prm.pw.w[2 * k + 1] * f * sn;
+            f *= 2.f;
+          }
+        }
 #pragma unroll
         for (int e = 0; e < 39; ++e) pe[e] *= kActScale;
       } else {
@@ -396,7 +444,7 @@ DevStatus* g_status = nullptr;  // one device-side status record per process (de
 }  // namespace
 
 static int launch_tc(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
-                     float* out_feat, int64_t P, int passes, int dbg_layer, float* dbg_out, int* status_host,
+                     float* out_feat, float* out_grad, int64_t P, int passes, int dbg_layer, float* dbg_out, int* status_host,
                      unsigned long long* trace, cudaStream_t st) {
   if (passes != 1 && passes != 3) return RECMV_E_DTYPE;
   PackedLayout L = packed_layout();
@@ -413,7 +461,9 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   }
   static bool attr_done[16] = {false};
   if (!attr_done[dev & 15]) {
-    cudaError_t e = cudaFuncSetAttribute(sdf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(sdf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(sdf_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     attr_done[dev & 15] = true;
   }
@@ -428,7 +478,7 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   prm.src = src; prm.pw = pw;
   prm.bias = (const float*)(pb + L.bias_all_off);
   prm.out_sdf = out_sdf; prm.out_feat = out_feat; prm.P = P; prm.passes = passes; prm.status = sd;
-  prm.dbg_layer = dbg_layer; prm.dbg_out = dbg_out; prm.trace = trace;
+  prm.dbg_layer = dbg_layer; prm.dbg_out = dbg_out; prm.trace = trace; prm.out_grad = out_grad;
   if (tc_.max_clusters == 0) {
     // clusters must fit inside a GPC: ask the driver how many 4-CTA clusters are co-resident and run
     // exactly that many (persistent kernel; a second wave would double the time)
@@ -441,14 +491,18 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
     at[0].val.clusterDim.x = 2 * kPairs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sdf_tc_kernel, &cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sdf_tc_kernel<false>, &cfg);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / (2 * kPairs) - 4; }
     tc_.max_clusters = n;
   }
-  int64_t tiles = (P + 127) / 128;
+  const int pts_per_tile = out_grad ? 32 : 128;
+  int64_t tiles = (P + pts_per_tile - 1) / pts_per_tile;
   int64_t want = (tiles + kPairs - 1) / kPairs;
   int clusters = (int)(want < tc_.max_clusters ? want : tc_.max_clusters);
-  sdf_tc_kernel<<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
+  if (out_grad)
+    sdf_tc_kernel<true><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
+  else
+    sdf_tc_kernel<false><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
   int s = launch_status();
   if (s) return s;
   if (status_host) {  // diagnostics path: synchronous read-back of the device status
@@ -463,7 +517,15 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
 
 int tc_sdf_forward(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
                    float* out_feat, int64_t P, int passes, cudaStream_t st) {
-  return launch_tc(src, packed, pw, out_sdf, out_feat, P, passes, -1, nullptr, nullptr, nullptr, st);
+  return launch_tc(src, packed, pw, out_sdf, out_feat, nullptr, P, passes, -1, nullptr, nullptr, nullptr, st);
+}
+
+int tc_sdf_forward_grad(const float* x, const void* packed, const PeWeights& pw, float* out_sdf, float* out_feat,
+                        float* out_grad, int64_t P, int passes, cudaStream_t st) {
+  PointSource src = {};
+  src.x = x;
+  src.S = 1;
+  return launch_tc(src, packed, pw, out_sdf, out_feat, out_grad, P, passes, -1, nullptr, nullptr, nullptr, st);
 }
 
 }  // namespace recmv
@@ -482,6 +544,6 @@ extern "C" int recmv_sdf_mlp_tc_debug(const float* x, const void* packed, const 
   src.S = 1;
   PeWeights pw;
   for (int i = 0; i < 12; ++i) pw.w[i] = pe_w[i];
-  return launch_tc(src, packed, pw, out_sdf, out_feat, P, passes, dbg_layer, dbg_out, status_host, trace,
+  return launch_tc(src, packed, pw, out_sdf, out_feat, nullptr, P, passes, dbg_layer, dbg_out, status_host, trace,
                    (cudaStream_t)stream);
 }

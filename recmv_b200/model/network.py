@@ -124,6 +124,24 @@ class ImplicitNetwork(nn.Module):
             self.rendcond = None
         return x
 
+    def value_and_grad(self, x, ratio, want_feat=False):
+        """Fused (sdf, d sdf/d x) without an autograd graph: what the Newton step of the surface solve and
+        inference-time normals need (utils/FindSurfacePs.py:176, OptimGarmentNetwork.py:3192).  One
+        forward-mode launch; `rendcond` is updated when want_feat."""
+        if not (self._fusable and x.is_cuda) or self.mlp_mode == ops.MLP_FP32_SIMT:
+            xg = x.detach().clone().requires_grad_(True)
+            with torch.enable_grad():
+                y = self._forward_graph(xg, ratio)
+                g = torch.autograd.grad(y.sum(), xg)[0]
+            self.last_path = "autograd-composite"
+            return y.detach(), g
+        self.last_path = "fused-jvp"
+        sdf, grad, feat = ops.sdf_value_and_grad(x.reshape(-1, 3), self.packed_weights(), self._pe_weights(ratio),
+                                                 self.mlp_mode, want_feat)
+        if want_feat:
+            self.rendcond = feat
+        return sdf, grad
+
     def gradient(self, x, y=None):
         x.requires_grad_(True)
         if y is None:

@@ -350,6 +350,23 @@ def sdf_mlp_forward(x, packed, pe_w=None, mode=None, want_feat=True):
     return sdf, feat
 
 
+def sdf_value_and_grad(x, packed, pe_w=None, mode=None, want_feat=False):
+    """(sdf [P,1], d sdf/d x [P,3], feat or None) in ONE forward-mode launch (no graph is recorded)."""
+    mode = DEFAULT_MLP_MODE if mode is None else mode
+    if mode == MLP_FP32_SIMT:
+        raise _lib.RecmvError("the fused value+gradient launch exists for the tcgen05 modes only")
+    x = x.contiguous().float()
+    _check_input(x, "x")
+    P = x.shape[0]
+    sdf = torch.empty((P, 1), dtype=torch.float32, device=x.device)
+    grad = torch.empty((P, 3), dtype=torch.float32, device=x.device)
+    feat = torch.empty((P, 256), dtype=torch.float32, device=x.device) if want_feat else None
+    with torch.cuda.device(x.device):
+        check(_lib.load().recmv_sdf_mlp_fwd_grad(_ptr(x), _ptr(packed), _pe_array(pe_w), _ptr(sdf), _ptr(feat),
+                                                 _ptr(grad), P, mode, _stream(x)), "recmv_sdf_mlp_fwd_grad")
+    return sdf, grad, feat
+
+
 def make_raymarch(cam_pos, t_near, t_far, samples):
     rm = RayMarch()
     rm.cam_pos = (c_float * 3)(*[float(c) for c in cam_pos])

@@ -52,12 +52,23 @@ def _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthresho
         if sel.numel() == 0:
             break
         cur = initTmpPs[sel].detach().clone().requires_grad_(True)
-        loss1 = tmpSdf(cur, ratio).abs().view(-1)
+        fused = getattr(tmpSdf, "value_and_grad", None) is not None
+        if fused:
+            # |f| term analytically from the fused forward-mode launch: d|f|/dp = sign(f) grad f
+            f, gf = tmpSdf.value_and_grad(cur.detach(), ratio)
+            loss1 = f.abs().view(-1)
+        else:
+            loss1 = tmpSdf(cur, ratio).abs().view(-1)
         direct = deform(cur, batch_inds[sel]) - cam
         up = torch.cross(direct, rays[sel], dim=1)
         loss2 = (up.norm(dim=1) / direct.norm(dim=1)).abs()
         loss = w1 * loss1 + w2 * loss2
-        grad = torch.autograd.grad(loss.sum(), cur, retain_graph=False, create_graph=False, only_inputs=True)[0]
+        if fused:
+            grad = torch.autograd.grad((w2 * loss2).sum(), cur, retain_graph=False, create_graph=False)[0]
+            grad = grad + w1 * torch.sign(f) * gf
+            loss = loss.detach()
+        else:
+            grad = torch.autograd.grad(loss.sum(), cur, retain_graph=False, create_graph=False, only_inputs=True)[0]
         t = -loss / (grad * grad).sum(1)
         cur = (cur + t.view(-1, 1) * grad).detach()
         initTmpPs[sel] = cur
