@@ -244,6 +244,26 @@ def main():
     h2d = dirs_h.numel() * 4 + A_h.numel() * 4 + t_h.numel() * 4
     d2h = o_t.numel() * 4 + o_i.numel() * 4
 
+    # ---- second half of the BASELINE metric: marching-cubes cells/s on a 257^3 grid (256^3 cells) -----------
+    mc = None
+    if rank == 0:
+        grid = synth.sphere_sdf_grid(257, num=8, seed=3, device=dev)
+        for _ in range(3):
+            v, f = ops.mc_gpu(grid, 2 / 256, 2 / 256, 2 / 256, -1.0, -1.0, -1.0, 0.0)
+        torch.cuda.synchronize(dev)
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            v, f = ops.mc_gpu(grid, 2 / 256, 2 / 256, 2 / 256, -1.0, -1.0, -1.0, 0.0)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        mc_ms = e0.elapsed_time(e1) / reps
+        mc_bytes = 4 * 257 ** 3 + 12 * v.shape[0] + 24 * f.shape[0]   # SURVEY 8d algorithmic bytes
+        mc = {"cells_per_s": 256 ** 3 / (mc_ms * 1e-3), "ms_per_call": mc_ms, "grid": "257^3", "verts": int(v.shape[0]),
+              "faces": int(f.shape[0]), "algorithmic_bytes": mc_bytes,
+              "note": "count + scan + D2H of (V,F) + allocate + vertex + face passes, end to end per call"}
+
     if rank == 0:
         peaks, src = measured_peaks()
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
@@ -285,7 +305,12 @@ def main():
                            "hits": nhit},
                 "clocks": sampler.summary(), "gpu_launches": launches,
                 "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "cpu_baseline": cpu, "mc": mc}
+        if mc is not None:
+            hbm = float(peaks.get("hbm_gbs", 6650.0))
+            mc["roofline"] = {"bound": "hbm", "achieved": mc["algorithmic_bytes"] / (mc["ms_per_call"] * 1e-3) / 1e9,
+                              "peak": hbm, "unit": "GB/s",
+                              "frac": mc["algorithmic_bytes"] / (mc["ms_per_call"] * 1e-3) / 1e9 / hbm}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
