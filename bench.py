@@ -27,6 +27,10 @@ S = 64
 FLOP_PER_SAMPLE = 2 * 1966592  # 3 933 184 FLOP per SDF forward
 METRIC = "rays/sec at 512x512x64-samp SDF render"
 MODES = {"simt": 0, "tc3": 1, "tc1": 2}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE full-frame launch of the dominant kernel, from the
+# `ncu --set full` capture summarised in profiles/r01_ncu_summary.md (141.7 MB read + 52.0 MB written; the
+# algorithmic minimum is the 67 MB sdf output + the touched part of the 181 MB voxel + 8.6 MB of weights)
+TRAFFIC_BYTES = {"tc3": 193699072}
 
 
 def measured_peaks():
@@ -271,7 +275,7 @@ def main():
         ach = flop / (kernel_ms * 1e-3) / 1e12
         issued = {0: None, 1: 3, 2: 1}[mode]
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": TRAFFIC_BYTES.get(args.mode), "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "kernel_ms": kernel_ms, "algorithmic_flop_per_launch": flop,
                 "mma_passes": issued,
                 "issued_frac": (ach * issued / peak_tf) if issued else None,

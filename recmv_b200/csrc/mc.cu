@@ -28,6 +28,9 @@ struct McTables {
   signed char owner[12][4];  // owning voxel offset + axis of every cube edge
 };
 __constant__ McTables c_mc;
+// copy of the triangle table in global memory: the face kernel indexes it with per-thread case numbers, and
+// divergent __constant__ reads serialise 32-way (L1-cached global loads do not)
+__device__ signed char g_mc_tri[256][16];
 
 static void build_tables(McTables& t) {
   for (int c = 0; c < 256; ++c) {
@@ -56,6 +59,8 @@ static int ensure_tables() {
     static McTables host;
     build_tables(host);
     cudaError_t e = cudaMemcpyToSymbol(c_mc, &host, sizeof(McTables));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_mc_tri, host.tri, sizeof(host.tri));
     if (e != cudaSuccess) return (int)e;
     dev_done[dev] = 1;
   }
@@ -98,28 +103,35 @@ __global__ void __launch_bounds__(kMcThreads) mc_count_kernel(const float* __res
                                                               int NY, int NZ, float iso,
                                                               unsigned char* __restrict__ cube,
                                                               int2* __restrict__ block_sums) {
-  __shared__ int2 tot;
-  int64_t N = (int64_t)NX * NY * NZ;
-  int64_t idx = (int64_t)blockIdx.x * kMcThreads + threadIdx.x;
-  int2 cnt = make_int2(0, 0);
+  __shared__ int s_cnt[2];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
+  const unsigned idx = blockIdx.x * kMcThreads + threadIdx.x;
+  int nv = 0, nt = 0;
   if (idx < N) {
-    int i = (int)(idx / ((int64_t)NY * NZ));
-    int rem = (int)(idx - (int64_t)i * NY * NZ);
-    int j = rem / NZ, k = rem - j * NZ;
+    const unsigned i = idx / plane, rem = idx - i * plane;
+    const unsigned j = rem / NZ, k = rem - j * NZ;
     int ci = 0;
-    if (i < NX - 1 && j < NY - 1 && k < NZ - 1) {
+    if (i < (unsigned)NX - 1 && j < (unsigned)NY - 1 && k < (unsigned)NZ - 1) {
       const float* p = sdf + idx;
-      size_t sj = NZ, si = (size_t)NY * NZ;
+      const size_t sj = NZ, si = plane;
       float v0 = __ldg(p), v1 = __ldg(p + si), v2 = __ldg(p + si + sj), v3 = __ldg(p + sj);
       float v4 = __ldg(p + 1), v5 = __ldg(p + si + 1), v6 = __ldg(p + si + sj + 1), v7 = __ldg(p + sj + 1);
       ci = (v0 < iso) | ((v1 < iso) << 1) | ((v2 < iso) << 2) | ((v3 < iso) << 3) | ((v4 < iso) << 4) |
            ((v5 < iso) << 5) | ((v6 < iso) << 6) | ((v7 < iso) << 7);
-      cnt = make_int2(c_mc.vinfo[ci] >> 6, c_mc.ntri[ci]);
+      if (ci != 0 && ci != 255) { nv = c_mc.vinfo[ci] >> 6; nt = c_mc.ntri[ci]; }
     }
     cube[idx] = (unsigned char)ci;
   }
-  block_excl_scan(cnt, &tot);
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+  // only the per-CTA totals are needed here: warp reduction, one shared atomic per non-empty warp
+  const int packed = __reduce_add_sync(0xffffffffu, nv | (nt << 16));
+  if ((threadIdx.x & 31) == 0 && packed) {
+    atomicAdd(&s_cnt[0], packed & 0xffff);
+    atomicAdd(&s_cnt[1], packed >> 16);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = make_int2(s_cnt[0], s_cnt[1]);
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_scan_kernel(int2* __restrict__ block_sums, int nb,
@@ -151,18 +163,18 @@ __global__ void __launch_bounds__(kMcThreads) mc_vertex_kernel(
     int* __restrict__ cellinfo, float sx, float sy, float sz, float ox, float oy, float oz,
     float* __restrict__ verts) {
   __shared__ int2 tot;
-  int64_t N = (int64_t)NX * NY * NZ;
-  int64_t idx = (int64_t)blockIdx.x * kMcThreads + threadIdx.x;
+  const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
+  const unsigned idx = blockIdx.x * kMcThreads + threadIdx.x;
   int ci = idx < N ? cube[idx] : 0;
-  int info = c_mc.vinfo[ci];
+  int info = (ci != 0 && ci != 255) ? c_mc.vinfo[ci] : (3 | (3 << 2) | (3 << 4));
   int nv = info >> 6;
+  if (!__syncthreads_or(nv > 0)) return;  // ~98 % of the CTAs hold no surface cell
   int2 ex = block_excl_scan(make_int2(nv, 0), &tot);
   if (nv == 0) return;
   int vbase = block_offs[blockIdx.x].x + ex.x;
   cellinfo[idx] = (vbase << 6) | (info & 63);
-  int i = (int)(idx / ((int64_t)NY * NZ));
-  int rem = (int)(idx - (int64_t)i * NY * NZ);
-  int j = rem / NZ, k = rem - j * NZ;
+  const unsigned i = idx / plane, rem = idx - i * plane;
+  const unsigned j = rem / NZ, k = rem - j * NZ;
   const float* p = sdf + idx;
   float v0 = __ldg(p);
   float fX = (float)i, fY = (float)j, fZ = (float)k;
@@ -190,25 +202,21 @@ __global__ void __launch_bounds__(kMcThreads) mc_face_kernel(int NX, int NY, int
                                                              const int* __restrict__ cellinfo,
                                                              long long* __restrict__ faces) {
   __shared__ int2 tot;
-  __shared__ signed char s_tri[256][16];
-  __shared__ signed char s_owner[12][4];
-  for (int q = threadIdx.x; q < 256 * 16; q += kMcThreads) (&s_tri[0][0])[q] = (&c_mc.tri[0][0])[q];
-  if (threadIdx.x < 48) (&s_owner[0][0])[threadIdx.x] = (&c_mc.owner[0][0])[threadIdx.x];
-  int64_t N = (int64_t)NX * NY * NZ;
-  int64_t idx = (int64_t)blockIdx.x * kMcThreads + threadIdx.x;
+  const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
+  const unsigned idx = blockIdx.x * kMcThreads + threadIdx.x;
   int ci = idx < N ? cube[idx] : 0;
-  int nt = c_mc.ntri[ci];
-  int2 ex = block_excl_scan(make_int2(0, nt), &tot);  // also orders the smem table fill
+  int nt = (ci != 0 && ci != 255) ? c_mc.ntri[ci] : 0;
+  if (!__syncthreads_or(nt > 0)) return;
+  int2 ex = block_excl_scan(make_int2(0, nt), &tot);
   if (nt == 0) return;
   int64_t fbase = (int64_t)block_offs[blockIdx.x].y + ex.y;
-  int i = (int)(idx / ((int64_t)NY * NZ));
-  int rem = (int)(idx - (int64_t)i * NY * NZ);
-  int j = rem / NZ, k = rem - j * NZ;
+  const int i = (int)(idx / plane), rem = (int)(idx - (unsigned)i * plane);
+  const int j = rem / NZ, k = rem - j * NZ;
   for (int t = 0; t < nt; ++t) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      int e = s_tri[ci][3 * t + c];
-      int oi = i + s_owner[e][0], oj = j + s_owner[e][1], ok = k + s_owner[e][2], d = s_owner[e][3];
+      int e = g_mc_tri[ci][3 * t + c];
+      int oi = i + c_mc.owner[e][0], oj = j + c_mc.owner[e][1], ok = k + c_mc.owner[e][2], d = c_mc.owner[e][3];
       long long vid = -1;
       if (oi < NX - 1 && oj < NY - 1 && ok < NZ - 1) {
         int info = cellinfo[((int64_t)oi * NY + oj) * NZ + ok];
