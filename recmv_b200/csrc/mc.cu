@@ -21,6 +21,25 @@ namespace recmv {
 
 constexpr int kMcThreads = 1024;
 
+// Division of a 31-bit index by a runtime constant through a precomputed multiplier (Granlund-Montgomery):
+// the per-cell (i,j,k) decomposition otherwise costs two ~20-instruction integer divisions per cell.
+struct FastDiv {
+  unsigned d, m, s;
+  __host__ static FastDiv make(unsigned d) {
+    FastDiv f;
+    f.d = d;
+    unsigned s = 0;
+    while ((1ull << s) < d) ++s;
+    f.s = s;
+    f.m = (unsigned)(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+    return f;
+  }
+  __device__ __forceinline__ unsigned div(unsigned n) const {
+    unsigned t = __umulhi(m, n);
+    return (t + n) >> s;  // n < 2^31 and t <= n: no overflow
+  }
+};
+
 struct McTables {
   signed char tri[256][16];
   unsigned char ntri[256];
@@ -102,16 +121,18 @@ __device__ __forceinline__ int2 block_excl_scan(int2 v, int2* tot) {
 __global__ void __launch_bounds__(kMcThreads) mc_count_kernel(const float* __restrict__ sdf, int NX,
                                                               int NY, int NZ, float iso,
                                                               unsigned char* __restrict__ cube,
-                                                              int2* __restrict__ block_sums) {
+                                                              int2* __restrict__ block_sums, int nseg,
+                                                              FastDiv dplane, FastDiv dnz) {
   __shared__ int s_cnt[2];
+  const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
+ for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {  // one 1024-cell segment per iteration
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
-  const unsigned idx = blockIdx.x * kMcThreads + threadIdx.x;
+  const unsigned idx = (unsigned)seg * kMcThreads + threadIdx.x;
   int nv = 0, nt = 0;
   if (idx < N) {
-    const unsigned i = idx / plane, rem = idx - i * plane;
-    const unsigned j = rem / NZ, k = rem - j * NZ;
+    const unsigned i = dplane.div(idx), rem = idx - i * plane;
+    const unsigned j = dnz.div(rem), k = rem - j * NZ;
     int ci = 0;
     if (i < (unsigned)NX - 1 && j < (unsigned)NY - 1 && k < (unsigned)NZ - 1) {
       const float* p = sdf + idx;
@@ -131,7 +152,9 @@ __global__ void __launch_bounds__(kMcThreads) mc_count_kernel(const float* __res
     atomicAdd(&s_cnt[1], packed >> 16);
   }
   __syncthreads();
-  if (threadIdx.x == 0) block_sums[blockIdx.x] = make_int2(s_cnt[0], s_cnt[1]);
+  if (threadIdx.x == 0) block_sums[seg] = make_int2(s_cnt[0], s_cnt[1]);
+  __syncthreads();
+ }
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_scan_kernel(int2* __restrict__ block_sums, int nb,
@@ -161,20 +184,21 @@ __global__ void __launch_bounds__(kMcThreads) mc_vertex_kernel(
     const float* __restrict__ sdf, int NX, int NY, int NZ, float iso,
     const unsigned char* __restrict__ cube, const int2* __restrict__ block_offs,
     int* __restrict__ cellinfo, float sx, float sy, float sz, float ox, float oy, float oz,
-    float* __restrict__ verts) {
+    float* __restrict__ verts, int nseg, FastDiv dplane, FastDiv dnz) {
   __shared__ int2 tot;
   const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
-  const unsigned idx = blockIdx.x * kMcThreads + threadIdx.x;
+ for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+  const unsigned idx = (unsigned)seg * kMcThreads + threadIdx.x;
   int ci = idx < N ? cube[idx] : 0;
   int info = (ci != 0 && ci != 255) ? c_mc.vinfo[ci] : (3 | (3 << 2) | (3 << 4));
   int nv = info >> 6;
-  if (!__syncthreads_or(nv > 0)) return;  // ~98 % of the CTAs hold no surface cell
+  if (!__syncthreads_or(nv > 0)) continue;  // ~98 % of the segments hold no surface cell
   int2 ex = block_excl_scan(make_int2(nv, 0), &tot);
-  if (nv == 0) return;
-  int vbase = block_offs[blockIdx.x].x + ex.x;
+  if (nv == 0) continue;
+  int vbase = block_offs[seg].x + ex.x;
   cellinfo[idx] = (vbase << 6) | (info & 63);
-  const unsigned i = idx / plane, rem = idx - i * plane;
-  const unsigned j = rem / NZ, k = rem - j * NZ;
+  const unsigned i = dplane.div(idx), rem = idx - i * plane;
+  const unsigned j = dnz.div(rem), k = rem - j * NZ;
   const float* p = sdf + idx;
   float v0 = __ldg(p);
   float fX = (float)i, fY = (float)j, fZ = (float)k;
@@ -194,24 +218,27 @@ __global__ void __launch_bounds__(kMcThreads) mc_vertex_kernel(
     float* o = verts + (size_t)(vbase + r8) * 3;
     o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ + off, sz, oz);
   }
+ }
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_face_kernel(int NX, int NY, int NZ,
                                                              const unsigned char* __restrict__ cube,
                                                              const int2* __restrict__ block_offs,
                                                              const int* __restrict__ cellinfo,
-                                                             long long* __restrict__ faces) {
+                                                             long long* __restrict__ faces, int nseg,
+                                                             FastDiv dplane, FastDiv dnz) {
   __shared__ int2 tot;
   const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
-  const unsigned idx = blockIdx.x * kMcThreads + threadIdx.x;
+ for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+  const unsigned idx = (unsigned)seg * kMcThreads + threadIdx.x;
   int ci = idx < N ? cube[idx] : 0;
   int nt = (ci != 0 && ci != 255) ? c_mc.ntri[ci] : 0;
-  if (!__syncthreads_or(nt > 0)) return;
+  if (!__syncthreads_or(nt > 0)) continue;
   int2 ex = block_excl_scan(make_int2(0, nt), &tot);
-  if (nt == 0) return;
-  int64_t fbase = (int64_t)block_offs[blockIdx.x].y + ex.y;
-  const int i = (int)(idx / plane), rem = (int)(idx - (unsigned)i * plane);
-  const int j = rem / NZ, k = rem - j * NZ;
+  if (nt == 0) continue;
+  int64_t fbase = (int64_t)block_offs[seg].y + ex.y;
+  const int i = (int)dplane.div(idx), rem = (int)(idx - (unsigned)i * plane);
+  const int j = (int)dnz.div((unsigned)rem), k = rem - j * NZ;
   for (int t = 0; t < nt; ++t) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -225,6 +252,7 @@ __global__ void __launch_bounds__(kMcThreads) mc_face_kernel(int NX, int NY, int
       faces[(fbase + t) * 3 + (2 - c)] = vid;  // reversed winding (CudaKernels.cu:502)
     }
   }
+ }
 }
 
 struct McScratch {
@@ -272,7 +300,9 @@ extern "C" int recmv_mc_count(const float* sdf, int NX, int NY, int NZ, float is
   if (s) return s;
   cudaStream_t st = (cudaStream_t)stream;
   McScratch sc = carve(scratch, NX, NY, NZ);
-  mc_count_kernel<<<sc.nb, kMcThreads, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums);
+  const int grid = sc.nb < 2 * num_sms() ? sc.nb : 2 * num_sms();
+  const FastDiv dplane = FastDiv::make((unsigned)NY * NZ), dnz = FastDiv::make((unsigned)NZ);
+  mc_count_kernel<<<grid, kMcThreads, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums, sc.nb, dplane, dnz);
   s = launch_status();
   if (s) return s;
   mc_scan_kernel<<<1, kMcThreads, 0, st>>>(sc.block_sums, sc.nb, sc.totals);
@@ -297,17 +327,19 @@ extern "C" int recmv_mc_emit(const float* sdf, int NX, int NY, int NZ, float iso
   if (s) return s;
   cudaStream_t st = (cudaStream_t)stream;
   McScratch sc = carve(scratch, NX, NY, NZ);
+  const int grid = sc.nb < 2 * num_sms() ? sc.nb : 2 * num_sms();
+  const FastDiv dplane = FastDiv::make((unsigned)NY * NZ), dnz = FastDiv::make((unsigned)NZ);
   if (verts) {
-    mc_vertex_kernel<<<sc.nb, kMcThreads, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums,
-                                                   sc.cellinfo, step[0], step[1], step[2], origin[0],
-                                                   origin[1], origin[2], verts);
+    mc_vertex_kernel<<<grid, kMcThreads, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums,
+                                                  sc.cellinfo, step[0], step[1], step[2], origin[0],
+                                                  origin[1], origin[2], verts, sc.nb, dplane, dnz);
     s = launch_status();
     if (s) return s;
   }
   if (faces) {
     if (!verts) return RECMV_E_NULL;  // faces need the packed words written by the vertex pass
-    mc_face_kernel<<<sc.nb, kMcThreads, 0, st>>>(NX, NY, NZ, sc.cube, sc.block_sums, sc.cellinfo,
-                                                 (long long*)faces);
+    mc_face_kernel<<<grid, kMcThreads, 0, st>>>(NX, NY, NZ, sc.cube, sc.block_sums, sc.cellinfo,
+                                                (long long*)faces, sc.nb, dplane, dnz);
     s = launch_status();
     if (s) return s;
   }
