@@ -217,6 +217,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     launches = ops.launch_count() - launches0
+    ops.check_async_errors()
     sampler.stop_flag = True
     step_ms = [a.elapsed_time(b) for a, b in ev]
     tt = torch.tensor([wall], dtype=torch.float64, device=dev)

@@ -33,7 +33,8 @@ enum {
   RECMV_E_DTYPE = -2,     /* dtype / layout / mode flag unknown  */
   RECMV_E_SHAPE = -3,     /* non-positive or inconsistent extent */
   RECMV_E_RANGE = -4,     /* size exceeds an implementation limit (e.g. > 2^26 MC vertices) */
-  RECMV_E_UNSUPPORTED = -5
+  RECMV_E_UNSUPPORTED = -5,
+  RECMV_E_DEVICE = -6     /* a tcgen05 launch aborted on a bounded mbarrier wait (see recmv_check_async_errors) */
 };
 
 enum { RECMV_F32 = 0, RECMV_F64 = 1 };
@@ -144,6 +145,11 @@ RECMV_API int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float*
 RECMV_API int recmv_sdf_mlp_fwd_grad(const float* x, const void* packed, const float* pe_w /*host*/,
                            float* out_sdf, float* out_feat, float* out_grad, int64_t P, int mode,
                            recmv_stream_t stream);
+
+/* Non-blocking health check of the tcgen05 path on the current device: every mbarrier wait in the kernel is
+ * bounded; a wait that times out records {code, barrier tag, block} in mapped host memory and later launches
+ * are refused with RECMV_E_DEVICE.  info may be NULL; clear != 0 resets the record.                        */
+RECMV_API int recmv_check_async_errors(int* info /*host [3]*/, int clear);
 
 /* Diagnostics for the tcgen05 path (used by tests/test_gpu_tc_bringup.py): same computation as
  * recmv_sdf_mlp_fwd in a TC mode (passes = 1 or 3), plus status_host[4] = {code, barrier tag, block, 0}

@@ -62,6 +62,7 @@ SIGNATURES = {
                                   c_int, c_void_p]),
     "recmv_sdf_mlp_fwd_grad": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_void_p, c_int64,
                                        c_int, c_void_p]),
+    "recmv_check_async_errors": (c_int, [POINTER(c_int), c_int]),
     "recmv_sdf_mlp_tc_debug": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int64,
                                        c_int, c_int, c_void_p, POINTER(c_int), c_void_p, c_void_p]),
     "recmv_render_sdf": (c_int, [c_void_p, POINTER(RayMarch), c_void_p, c_void_p, c_void_p, c_int64,

@@ -17,6 +17,7 @@ extern "C" const char* recmv_error_string(int status) {
     case RECMV_E_SHAPE: return "non-positive, misaligned or inconsistent extent";
     case RECMV_E_RANGE: return "size exceeds an implementation limit";
     case RECMV_E_UNSUPPORTED: return "not supported by this build";
+    case RECMV_E_DEVICE: return "a previous tcgen05 launch aborted on a bounded mbarrier wait (recmv_check_async_errors)";
     default: break;
   }
   if (status > 0) return cudaGetErrorString((cudaError_t)status);

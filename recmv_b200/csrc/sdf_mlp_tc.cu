@@ -435,12 +435,25 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
 }
 
 namespace {
+DevStatus* g_status_host[16] = {nullptr};
+
+// one mapped, pinned status record per device
+int tc_status_record(int dev, DevStatus** out) {
+  DevStatus*& h = g_status_host[dev & 15];
+  if (!h) {
+    cudaError_t e = cudaHostAlloc((void**)&h, sizeof(DevStatus), cudaHostAllocMapped);
+    if (e != cudaSuccess) return (int)e;
+    h->code = 0; h->detail = 0; h->block = 0; h->pad = 0;
+  }
+  *out = h;
+  return 0;
+}
+
 struct TmapCache {
   const void* base = nullptr;
   CUtensorMap m128;
   int max_clusters = 0;
 };
-DevStatus* g_status = nullptr;  // one device-side status record per process (device 0..n share: reset per launch)
 }  // namespace
 
 static int launch_tc(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
@@ -467,13 +480,12 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
     if (e != cudaSuccess) return (int)e;
     attr_done[dev & 15] = true;
   }
-  static DevStatus* status_dev[16] = {nullptr};
-  if (!status_dev[dev & 15]) {
-    cudaError_t e = cudaMalloc(&status_dev[dev & 15], sizeof(DevStatus));
-    if (e != cudaSuccess) return (int)e;
-  }
-  DevStatus* sd = status_dev[dev & 15];
-  cudaMemsetAsync(sd, 0, sizeof(DevStatus), st);
+  // Device status record in MAPPED pinned host memory: a bounded wait that times out writes it there, the
+  // host sees it without a synchronisation and refuses further work (recmv_check_async_errors()).
+  DevStatus* sd = nullptr;
+  int s0 = tc_status_record(dev, &sd);
+  if (s0) return s0;
+  if (sd->code != 0) return RECMV_E_DEVICE;  // a previous launch on this device aborted
   TcParams prm;
   prm.src = src; prm.pw = pw;
   prm.bias = (const float*)(pb + L.bias_all_off);
@@ -505,12 +517,11 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
     sdf_tc_kernel<false><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
   int s = launch_status();
   if (s) return s;
-  if (status_host) {  // diagnostics path: synchronous read-back of the device status
-    DevStatus h;
-    cudaError_t e = cudaMemcpyAsync(&h, sd, sizeof(h), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (status_host) {  // diagnostics path: wait for the launch, then report (and clear) the status record
+    cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return (int)e;
-    status_host[0] = h.code; status_host[1] = h.detail; status_host[2] = h.block; status_host[3] = 0;
+    status_host[0] = sd->code; status_host[1] = sd->detail; status_host[2] = sd->block; status_host[3] = 0;
+    sd->code = 0; sd->detail = 0; sd->block = 0;
   }
   return RECMV_OK;
 }
@@ -531,6 +542,21 @@ int tc_sdf_forward_grad(const float* x, const void* packed, const PeWeights& pw,
 }  // namespace recmv
 
 using namespace recmv;
+
+// Reports (without synchronising) whether any tcgen05 launch on the current device has aborted on a bounded
+// wait since the last check: 0 = none, RECMV_E_DEVICE otherwise; info[3] = {code, barrier tag, block}.
+extern "C" int recmv_check_async_errors(int* info, int clear) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevStatus* h = g_status_host[dev & 15];
+  if (!h || h->code == 0) {
+    if (info) { info[0] = 0; info[1] = 0; info[2] = 0; }
+    return RECMV_OK;
+  }
+  if (info) { info[0] = h->code; info[1] = h->detail; info[2] = h->block; }
+  if (clear) { h->code = 0; h->detail = 0; h->block = 0; }
+  return RECMV_E_DEVICE;
+}
 
 // Diagnostics entry (see include/recmv_b200.h): runs the tcgen05 path on canonical points and returns
 // the device status record (which bounded wait timed out, if any) plus the raw accumulator of one layer.

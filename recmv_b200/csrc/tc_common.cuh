@@ -35,12 +35,6 @@ __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -49,9 +43,6 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // generic-proxy smem writes -> visible to the async proxy (TMA / tensor core operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 // Arrive on a barrier that lives in CTA `rank` of the cluster.  Default (release.cta) semantics, as
 // CUTLASS's ClusterBarrier does: the data these barriers guard is consumed through the async proxy
 // (tensor-core operand reads) after a fence.proxy.async by the writer.  The .release.cluster /
@@ -88,10 +79,14 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
     if (*abort_flag) return false;
     if (clock64() - t0 > 400000000LL) {  // ~0.2 s at 2 GHz
       *abort_flag = 1;
-      if (atomicCAS(&status->code, 0, 1) == 0) {
-        status->detail = tag;
-        status->block = blockIdx.x;
-      }
+      // status lives in mapped pinned host memory: plain system-visible stores (first writer wins is not
+      // needed -- any timed-out wait is a valid report)
+      volatile DevStatus* vs = status;
+      vs->detail = tag;
+      vs->block = blockIdx.x;
+      __threadfence_system();
+      vs->code = 1;
+      __threadfence_system();
       return false;
     }
   }
@@ -101,17 +96,7 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
-// 2-D tile load into THIS CTA's smem; completion bytes are signalled on `bar_cluster_addr`, a
-// shared::cluster address (the leader CTA's barrier for a CTA pair).
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr,
-                                                 int32_t c0, int32_t c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_dst), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
-}
-
-// Multicast variant: the tile lands at the same smem offset of every CTA in `mask`; with cta_group::2
+// 2-D tile load, multicast: the tile lands at the same smem offset of every CTA in `mask`; with cta_group::2
 // the completion bytes of each destination are signalled on the barrier (same offset) of the leader of
 // that destination's CTA pair.
 __device__ __forceinline__ void tma_load_2d_pair_mcast(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster_addr,

@@ -402,5 +402,13 @@ def render_sdf(ray_dirs, cam_pos, t_near, t_far, samples, A, trans, ws_cl, cente
     return sdf, xc, hit_idx, hit_t
 
 
+def check_async_errors(clear=False):
+    """Raise if a tcgen05 launch on the current device aborted on a bounded wait (non-blocking check)."""
+    info = (ctypes.c_int * 3)()
+    st = _lib.load().recmv_check_async_errors(info, 1 if clear else 0)
+    if st != 0:
+        raise _lib.RecmvError(f"tcgen05 kernel aborted: code={info[0]} barrier tag={info[1]} block={info[2]}")
+
+
 def launch_count():
     return int(_lib.load().recmv_launch_count())

@@ -39,6 +39,13 @@ def _supported(mode):
 _cache = {}
 
 
+@pytest.fixture(autouse=True)
+def _no_aborted_launch():
+    yield
+    torch.cuda.synchronize()
+    ops.check_async_errors()  # every mbarrier wait in the tcgen05 kernel is bounded; none may have timed out
+
+
 def _net(tag):
     if tag not in _cache:
         _cache[tag] = testing.build_sdf(getTmpSdf, seed=0, perturb_seed=None if tag == "geo" else 101).to(DEV)
