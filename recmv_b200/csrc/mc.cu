@@ -118,43 +118,57 @@ __device__ __forceinline__ int2 block_excl_scan(int2 v, int2* tot) {
   return r;
 }
 
-__global__ void __launch_bounds__(kMcThreads) mc_count_kernel(const float* __restrict__ sdf, int NX,
-                                                              int NY, int NZ, float iso,
-                                                              unsigned char* __restrict__ cube,
-                                                              int2* __restrict__ block_sums, int nseg,
-                                                              FastDiv dplane, FastDiv dnz) {
-  __shared__ int s_cnt[2];
+constexpr int kMcWarpBlock = 256;  // 8 warps per CTA in the warp-per-segment passes
+
+// Pass 1, one WARP per 1024-cell segment, 32 rows of 32 consecutive cells: 4 coalesced loads per cell (its
+// four z-columns at k); the k+1 values come from the next lane by shuffle (lane 31 loads them).  No block
+// barrier, no shared memory.  Writes the 1-byte case index of every voxel and the segment's (verts, tris).
+__global__ void __launch_bounds__(kMcWarpBlock) mc_count_kernel(const float* __restrict__ sdf, int NX,
+                                                                int NY, int NZ, float iso,
+                                                                unsigned char* __restrict__ cube,
+                                                                int2* __restrict__ block_sums, int nseg,
+                                                                FastDiv dplane, FastDiv dnz) {
   const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
- for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {  // one 1024-cell segment per iteration
-  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const unsigned idx = (unsigned)seg * kMcThreads + threadIdx.x;
-  int nv = 0, nt = 0;
-  if (idx < N) {
-    const unsigned i = dplane.div(idx), rem = idx - i * plane;
-    const unsigned j = dnz.div(rem), k = rem - j * NZ;
-    int ci = 0;
-    if (i < (unsigned)NX - 1 && j < (unsigned)NY - 1 && k < (unsigned)NZ - 1) {
-      const float* p = sdf + idx;
-      const size_t sj = NZ, si = plane;
-      float v0 = __ldg(p), v1 = __ldg(p + si), v2 = __ldg(p + si + sj), v3 = __ldg(p + sj);
-      float v4 = __ldg(p + 1), v5 = __ldg(p + si + 1), v6 = __ldg(p + si + sj + 1), v7 = __ldg(p + sj + 1);
-      ci = (v0 < iso) | ((v1 < iso) << 1) | ((v2 < iso) << 2) | ((v3 < iso) << 3) | ((v4 < iso) << 4) |
-           ((v5 < iso) << 5) | ((v6 < iso) << 6) | ((v7 < iso) << 7);
-      if (ci != 0 && ci != 255) { nv = c_mc.vinfo[ci] >> 6; nt = c_mc.ntri[ci]; }
+  const int lane = threadIdx.x & 31;
+  const int seg = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (seg >= nseg) return;
+  int acc = 0;  // verts | tris << 16 of this lane
+  const size_t sj = NZ, si = plane;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const unsigned idx = (unsigned)seg * kMcThreads + r * 32 + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // columns (i,j) (i+1,j) (i+1,j+1) (i,j+1) at k
+    bool cell = false;
+    unsigned i = 0, j = 0, k = 0;
+    if (idx < N) {
+      i = dplane.div(idx);
+      const unsigned rem = idx - i * plane;
+      j = dnz.div(rem);
+      k = rem - j * NZ;
+      const bool col = i < (unsigned)NX - 1 && j < (unsigned)NY - 1;
+      if (col) {
+        const float* p = sdf + idx;
+        a0 = __ldg(p); a1 = __ldg(p + si); a2 = __ldg(p + si + sj); a3 = __ldg(p + sj);
+      }
+      cell = col && k < (unsigned)NZ - 1;
     }
-    cube[idx] = (unsigned char)ci;
+    // k+1 values: lane+1 holds idx+1 (same column unless the row wraps, and then this cell is not a cell)
+    float b0 = __shfl_down_sync(0xffffffffu, a0, 1), b1 = __shfl_down_sync(0xffffffffu, a1, 1);
+    float b2 = __shfl_down_sync(0xffffffffu, a2, 1), b3 = __shfl_down_sync(0xffffffffu, a3, 1);
+    if (lane == 31 && cell) {
+      const float* p = sdf + idx + 1;
+      b0 = __ldg(p); b1 = __ldg(p + si); b2 = __ldg(p + si + sj); b3 = __ldg(p + sj);
+    }
+    int ci = 0;
+    if (cell) {
+      ci = (a0 < iso) | ((a1 < iso) << 1) | ((a2 < iso) << 2) | ((a3 < iso) << 3) | ((b0 < iso) << 4) |
+           ((b1 < iso) << 5) | ((b2 < iso) << 6) | ((b3 < iso) << 7);
+      if (ci != 0 && ci != 255) acc += (c_mc.vinfo[ci] >> 6) | ((int)c_mc.ntri[ci] << 16);
+    }
+    if (idx < N) cube[idx] = (unsigned char)ci;
   }
-  // only the per-CTA totals are needed here: warp reduction, one shared atomic per non-empty warp
-  const int packed = __reduce_add_sync(0xffffffffu, nv | (nt << 16));
-  if ((threadIdx.x & 31) == 0 && packed) {
-    atomicAdd(&s_cnt[0], packed & 0xffff);
-    atomicAdd(&s_cnt[1], packed >> 16);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) block_sums[seg] = make_int2(s_cnt[0], s_cnt[1]);
-  __syncthreads();
- }
+  const int tot = __reduce_add_sync(0xffffffffu, acc);
+  if (lane == 0) block_sums[seg] = make_int2(tot & 0xffff, tot >> 16);
 }
 
 __global__ void __launch_bounds__(kMcThreads) mc_scan_kernel(int2* __restrict__ block_sums, int nb,
@@ -180,79 +194,102 @@ __device__ __forceinline__ float edge_offset(float v1, float v2, float iso) {
   return (float)((double)(iso - v1) / d);
 }
 
-__global__ void __launch_bounds__(kMcThreads) mc_vertex_kernel(
+// warp-wide exclusive scan
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
+}
+
+// Passes 3 and 4, one warp per 1024-cell segment, 8 rows of 128 cells: each lane loads the case bytes of 4
+// consecutive cells as one 32-bit word; a row whose words are all 0x00000000 / 0xffffffff (no surface: ~98 %
+// of them) costs one load and one ballot.
+template <bool kFaces>
+__global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
     const float* __restrict__ sdf, int NX, int NY, int NZ, float iso,
     const unsigned char* __restrict__ cube, const int2* __restrict__ block_offs,
     int* __restrict__ cellinfo, float sx, float sy, float sz, float ox, float oy, float oz,
-    float* __restrict__ verts, int nseg, FastDiv dplane, FastDiv dnz) {
-  __shared__ int2 tot;
+    float* __restrict__ verts, long long* __restrict__ faces, int nseg, FastDiv dplane, FastDiv dnz) {
   const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
- for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-  const unsigned idx = (unsigned)seg * kMcThreads + threadIdx.x;
-  int ci = idx < N ? cube[idx] : 0;
-  int info = (ci != 0 && ci != 255) ? c_mc.vinfo[ci] : (3 | (3 << 2) | (3 << 4));
-  int nv = info >> 6;
-  if (!__syncthreads_or(nv > 0)) continue;  // ~98 % of the segments hold no surface cell
-  int2 ex = block_excl_scan(make_int2(nv, 0), &tot);
-  if (nv == 0) continue;
-  int vbase = block_offs[seg].x + ex.x;
-  cellinfo[idx] = (vbase << 6) | (info & 63);
-  const unsigned i = dplane.div(idx), rem = idx - i * plane;
-  const unsigned j = dnz.div(rem), k = rem - j * NZ;
-  const float* p = sdf + idx;
-  float v0 = __ldg(p);
-  float fX = (float)i, fY = (float)j, fZ = (float)k;
-  int r0 = info & 3, r3 = (info >> 2) & 3, r8 = (info >> 4) & 3;
-  if (r0 != 3) {  // edge 0: corner 0 -> 1, +x
-    float off = edge_offset(v0, __ldg(p + (size_t)NY * NZ), iso);
-    float* o = verts + (size_t)(vbase + r0) * 3;
-    o[0] = fmaf(fX + off, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ, sz, oz);
-  }
-  if (r3 != 3) {  // edge 3: corner 3 (0,1,0) -> 0, -y
-    float off = edge_offset(__ldg(p + NZ), v0, iso);
-    float* o = verts + (size_t)(vbase + r3) * 3;
-    o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY + (1.f - off), sy, oy); o[2] = fmaf(fZ, sz, oz);
-  }
-  if (r8 != 3) {  // edge 8: corner 0 -> 4, +z
-    float off = edge_offset(v0, __ldg(p + 1), iso);
-    float* o = verts + (size_t)(vbase + r8) * 3;
-    o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ + off, sz, oz);
-  }
- }
-}
-
-__global__ void __launch_bounds__(kMcThreads) mc_face_kernel(int NX, int NY, int NZ,
-                                                             const unsigned char* __restrict__ cube,
-                                                             const int2* __restrict__ block_offs,
-                                                             const int* __restrict__ cellinfo,
-                                                             long long* __restrict__ faces, int nseg,
-                                                             FastDiv dplane, FastDiv dnz) {
-  __shared__ int2 tot;
-  const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
- for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-  const unsigned idx = (unsigned)seg * kMcThreads + threadIdx.x;
-  int ci = idx < N ? cube[idx] : 0;
-  int nt = (ci != 0 && ci != 255) ? c_mc.ntri[ci] : 0;
-  if (!__syncthreads_or(nt > 0)) continue;
-  int2 ex = block_excl_scan(make_int2(0, nt), &tot);
-  if (nt == 0) continue;
-  int64_t fbase = (int64_t)block_offs[seg].y + ex.y;
-  const int i = (int)dplane.div(idx), rem = (int)(idx - (unsigned)i * plane);
-  const int j = (int)dnz.div((unsigned)rem), k = rem - j * NZ;
-  for (int t = 0; t < nt; ++t) {
+  const int lane = threadIdx.x & 31;
+  const int seg = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (seg >= nseg) return;
+  const int2 segoff = block_offs[seg];
+  if (!kFaces) { if (seg + 1 < nseg && block_offs[seg + 1].x == segoff.x) return; }   // nothing to emit here
+  else { if (seg + 1 < nseg && block_offs[seg + 1].y == segoff.y) return; }
+  int running = kFaces ? segoff.y : segoff.x;
+  for (int r = 0; r < 8; ++r) {
+    const unsigned idx0 = (unsigned)seg * kMcThreads + r * 128 + lane * 4;
+    unsigned word = 0;
+    if (idx0 + 3 < N) word = *reinterpret_cast<const unsigned*>(cube + idx0);   // N*1 bytes; idx0 % 4 == 0
+    else { for (int q = 0; q < 4; ++q) if (idx0 + q < N) word |= (unsigned)cube[idx0 + q] << (8 * q); }
+    if (__ballot_sync(0xffffffffu, word != 0u && word != 0xffffffffu) == 0u) continue;
+    int cnt[4], mine = 0;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      int e = g_mc_tri[ci][3 * t + c];
-      int oi = i + c_mc.owner[e][0], oj = j + c_mc.owner[e][1], ok = k + c_mc.owner[e][2], d = c_mc.owner[e][3];
-      long long vid = -1;
-      if (oi < NX - 1 && oj < NY - 1 && ok < NZ - 1) {
-        int info = cellinfo[((int64_t)oi * NY + oj) * NZ + ok];
-        vid = (long long)(info >> 6) + ((info >> (2 * d)) & 3);
+    for (int q = 0; q < 4; ++q) {
+      const int ci = (word >> (8 * q)) & 255;
+      cnt[q] = (ci != 0 && ci != 255) ? (kFaces ? (int)c_mc.ntri[ci] : (int)(c_mc.vinfo[ci] >> 6)) : 0;
+      mine += cnt[q];
+    }
+    int row_total;
+    int off = running + warp_excl_scan(mine, lane, &row_total);
+    running += row_total;
+    if (mine == 0) continue;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (cnt[q] == 0) continue;
+      const unsigned idx = idx0 + q;
+      const int ci = (word >> (8 * q)) & 255;
+      const int i = (int)dplane.div(idx), rem = (int)(idx - (unsigned)i * plane);
+      const int j = (int)dnz.div((unsigned)rem), k = rem - j * NZ;
+      if (!kFaces) {
+        const int info = c_mc.vinfo[ci];
+        const int vbase = off;
+        cellinfo[idx] = (vbase << 6) | (info & 63);
+        const float* p = sdf + idx;
+        const float v0 = __ldg(p);
+        const float fX = (float)i, fY = (float)j, fZ = (float)k;
+        const int r0 = info & 3, r3 = (info >> 2) & 3, r8 = (info >> 4) & 3;
+        if (r0 != 3) {  // edge 0: corner 0 -> 1, +x
+          const float o_ = edge_offset(v0, __ldg(p + plane), iso);
+          float* o = verts + (size_t)(vbase + r0) * 3;
+          o[0] = fmaf(fX + o_, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ, sz, oz);
+        }
+        if (r3 != 3) {  // edge 3: corner 3 (0,1,0) -> 0, -y
+          const float o_ = edge_offset(__ldg(p + NZ), v0, iso);
+          float* o = verts + (size_t)(vbase + r3) * 3;
+          o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY + (1.f - o_), sy, oy); o[2] = fmaf(fZ, sz, oz);
+        }
+        if (r8 != 3) {  // edge 8: corner 0 -> 4, +z
+          const float o_ = edge_offset(v0, __ldg(p + 1), iso);
+          float* o = verts + (size_t)(vbase + r8) * 3;
+          o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ + o_, sz, oz);
+        }
+      } else {
+        const long long fbase = off;
+        for (int t = 0; t < cnt[q]; ++t) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int e = g_mc_tri[ci][3 * t + c];
+            const int oi = i + c_mc.owner[e][0], oj = j + c_mc.owner[e][1], ok = k + c_mc.owner[e][2];
+            const int d = c_mc.owner[e][3];
+            long long vid = -1;
+            if (oi < NX - 1 && oj < NY - 1 && ok < NZ - 1) {
+              const int info = cellinfo[((int64_t)oi * NY + oj) * NZ + ok];
+              vid = (long long)(info >> 6) + ((info >> (2 * d)) & 3);
+            }
+            faces[(fbase + t) * 3 + (2 - c)] = vid;  // reversed winding (CudaKernels.cu:502)
+          }
+        }
       }
-      faces[(fbase + t) * 3 + (2 - c)] = vid;  // reversed winding (CudaKernels.cu:502)
+      off += cnt[q];
     }
   }
- }
 }
 
 struct McScratch {
@@ -300,9 +337,9 @@ extern "C" int recmv_mc_count(const float* sdf, int NX, int NY, int NZ, float is
   if (s) return s;
   cudaStream_t st = (cudaStream_t)stream;
   McScratch sc = carve(scratch, NX, NY, NZ);
-  const int grid = sc.nb < 2 * num_sms() ? sc.nb : 2 * num_sms();
+  const int grid = (sc.nb * 32 + kMcWarpBlock - 1) / kMcWarpBlock;  // one warp per 1024-cell segment
   const FastDiv dplane = FastDiv::make((unsigned)NY * NZ), dnz = FastDiv::make((unsigned)NZ);
-  mc_count_kernel<<<grid, kMcThreads, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums, sc.nb, dplane, dnz);
+  mc_count_kernel<<<grid, kMcWarpBlock, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums, sc.nb, dplane, dnz);
   s = launch_status();
   if (s) return s;
   mc_scan_kernel<<<1, kMcThreads, 0, st>>>(sc.block_sums, sc.nb, sc.totals);
@@ -327,19 +364,20 @@ extern "C" int recmv_mc_emit(const float* sdf, int NX, int NY, int NZ, float iso
   if (s) return s;
   cudaStream_t st = (cudaStream_t)stream;
   McScratch sc = carve(scratch, NX, NY, NZ);
-  const int grid = sc.nb < 2 * num_sms() ? sc.nb : 2 * num_sms();
+  const int grid = (sc.nb * 32 + kMcWarpBlock - 1) / kMcWarpBlock;
   const FastDiv dplane = FastDiv::make((unsigned)NY * NZ), dnz = FastDiv::make((unsigned)NZ);
   if (verts) {
-    mc_vertex_kernel<<<grid, kMcThreads, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums,
-                                                  sc.cellinfo, step[0], step[1], step[2], origin[0],
-                                                  origin[1], origin[2], verts, sc.nb, dplane, dnz);
+    mc_emit_kernel<false><<<grid, kMcWarpBlock, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums, sc.cellinfo,
+                                                         step[0], step[1], step[2], origin[0], origin[1], origin[2],
+                                                         verts, nullptr, sc.nb, dplane, dnz);
     s = launch_status();
     if (s) return s;
   }
   if (faces) {
     if (!verts) return RECMV_E_NULL;  // faces need the packed words written by the vertex pass
-    mc_face_kernel<<<grid, kMcThreads, 0, st>>>(NX, NY, NZ, sc.cube, sc.block_sums, sc.cellinfo,
-                                                (long long*)faces, sc.nb, dplane, dnz);
+    mc_emit_kernel<true><<<grid, kMcWarpBlock, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums, sc.cellinfo,
+                                                        0.f, 0.f, 0.f, 0.f, 0.f, 0.f, nullptr, (long long*)faces,
+                                                        sc.nb, dplane, dnz);
     s = launch_status();
     if (s) return s;
   }
