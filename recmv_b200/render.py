@@ -105,3 +105,62 @@ class SdfRenderer:
         out_hit_t_pinned.copy_(hit_t, non_blocking=True)
         out_hit_idx_pinned.copy_(hit_idx, non_blocking=True)
         return out_hit_t_pinned, out_hit_idx_pinned
+
+
+    # ---- full per-ray render: sdf march -> surface point -> normal -> colour --------------------------------
+    def surface_points(self, ray_dirs, A, trans, frame_of_ray=None, refine=3):
+        """Observation-space surface point per ray: first sign change of the 64-sample march, then `refine`
+        secant steps on the bracketing interval (each step = one inverse-LBS launch + one fused SDF launch on
+        the hit rays only).  Returns (hit mask [R], t [R], x_obs [R,3], x_can [R,3], sdf at the point [R])."""
+        R = ray_dirs.shape[0]
+        rpf = 0 if frame_of_ray is not None else R // max(int(A.shape[0]), 1)
+        sdf, _, hit_idx, hit_t = ops.render_sdf(ray_dirs, self.cam_pos, self.t_near, self.t_far, self.samples, A,
+                                                trans, self.ws_cl, synth.BBOX_CENTER, synth.BBOX_EXTEND,
+                                                self.packed, self.pe_w, self.mode, frame_of_ray, rpf, False, True)
+        hit = hit_idx > 0
+        idx = hit.nonzero(as_tuple=False).view(-1)
+        cam = torch.tensor(self.cam_pos, device=self.device, dtype=torch.float32)
+        dt = (self.t_far - self.t_near) / self.samples
+        k = hit_idx[idx].long()
+        t0 = self.t_near + (k.float() - 0.5) * dt          # sample k-1 (outside) .. sample k (inside)
+        t1 = t0 + dt
+        s0 = sdf[idx, k - 1]
+        s1 = sdf[idx, k]
+        d = ray_dirs[idx]
+        frames = (frame_of_ray[idx].long() if frame_of_ray is not None
+                  else torch.div(idx, max(rpf, 1), rounding_mode="floor").clamp_max(A.shape[0] - 1))
+
+        def eval_at(t):
+            xo = cam[None] + t[:, None] * d
+            xc, ok = ops.lbs_inverse(xo, A, trans, self.ws_cl, synth.BBOX_CENTER, synth.BBOX_EXTEND, frames, 0)
+            with torch.no_grad():
+                v = self.sdf_net(xc, None)[:, 0]
+            return xo, xc, torch.where(ok, v, torch.full_like(v, 1e10))
+        t = t0 + (t1 - t0) * s0 / (s0 - s1)
+        xo, xc, v = eval_at(t)
+        for _ in range(refine):
+            inside = v <= 0                                  # keep the root bracketed (regula falsi)
+            t1 = torch.where(inside, t, t1); s1 = torch.where(inside, v, s1)
+            t0 = torch.where(inside, t0, t); s0 = torch.where(inside, s0, v)
+            t = t0 + (t1 - t0) * s0 / (s0 - s1)
+            xo, xc, v = eval_at(t)
+        full = lambda z, fill: torch.full((R,) + z.shape[1:], fill, device=self.device, dtype=z.dtype).index_copy_(0, idx, z)  # noqa: E731
+        return hit, full(t, 0.0), full(xo, 0.0), full(xc, 0.0), full(v, 0.0)
+
+    def render_image(self, ray_dirs, A, trans, render_net, ratio=None, frame_of_ray=None, refine=3):
+        """RGB per ray (background 0): surface point -> canonical normal from the fused value+gradient launch
+        (which also returns the 256 features) -> IDR colour MLP on (x_can, normal, view dir, features).
+        The view direction is the observation-space ray (the reference pulls it back through the deformer's
+        Jacobian, utils/utils.py:232-250; that belongs to the training path)."""
+        hit, t, xo, xc, v = self.surface_points(ray_dirs, A, trans, frame_of_ray, refine)
+        idx = hit.nonzero(as_tuple=False).view(-1)
+        rgb = torch.zeros((ray_dirs.shape[0], 3), device=self.device)
+        if idx.numel() == 0:
+            return rgb, hit, t
+        _, grad = self.sdf_net.value_and_grad(xc[idx], ratio, want_feat=True)
+        n = torch.nn.functional.normalize(grad, dim=1)
+        with torch.no_grad():
+            col = render_net(xc[idx], n, ray_dirs[idx], self.sdf_net.rendcond,
+                             {"renderRatio": None if ratio is None else ratio.get("renderRatio")})
+        rgb.index_copy_(0, idx, col)
+        return rgb, hit, t

@@ -154,3 +154,35 @@ def test_fused_value_and_gradient_matches_reference_autograd(tag):
     s3, g3 = net.value_and_grad(x[:64], None)
     assert net.last_path == "autograd-composite" and norm_err(g3, g["grad_none"][:64]) < 2e-5
     net.mlp_mode = None
+
+
+def test_full_render_surface_normals_colour():
+    """End-to-end render from the fused pieces: refined surface points lie on the level set AND on their rays,
+    normals equal the reference-style autograd normals, colours equal the colour MLP on those inputs."""
+    from recmv_b200.model import RenderingNetwork_view_norm
+    from recmv_b200.render import SdfRenderer
+    net = _net("trained")
+    net.mlp_mode = _lib.MLP_TC_F16X3
+    ren = SdfRenderer(DEV, sdf_net=net, voxel_shape=(17, 33, 21), samples=64)
+    torch.manual_seed(2)
+    rn = RenderingNetwork_view_norm(256, d_in=9, d_out=3, dims=[512] * 4, mode="idr", weight_norm=True,
+                                    multires_v=4, multires_n=0).to(DEV)
+    poses, trans = synth.poses_trans(1, seed=11)
+    A, t = ren.bone_matrices(poses.to(DEV) * 0.3, trans.to(DEV))
+    dirs = synth.pinhole_rays(64, 64, device=DEV)
+    rgb, hit, th = ren.render_image(dirs, A, t, rn, ratio={"renderRatio": None})
+    hit2, t2, xo, xc, v = ren.surface_points(dirs, A, t)
+    assert hit.sum() > 300 and torch.equal(hit, hit2)
+    assert v[hit].abs().max() < 2e-4                      # on the zero level set after 3 regula-falsi steps
+    cam = torch.tensor(synth.CAM_POS, device=DEV)
+    assert ((cam[None] + t2[:, None] * dirs - xo)[hit]).abs().max() < 1e-5   # and on its ray
+    # normals / colour against the autograd-composite path on the same points
+    idx = hit.nonzero().view(-1)
+    p = xc[idx].clone().requires_grad_(True)
+    y = net(p, None)
+    g = torch.autograd.grad(y.sum(), p)[0]
+    n_ref = torch.nn.functional.normalize(g, dim=1)
+    with torch.no_grad():
+        col_ref = rn(xc[idx], n_ref, dirs[idx], net.rendcond.detach(), {"renderRatio": None})
+    assert (rgb[idx] - col_ref).abs().max() < 2e-3 and rgb[~hit].abs().max() == 0
+    net.mlp_mode = None
