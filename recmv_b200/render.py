@@ -157,10 +157,11 @@ class SdfRenderer:
         rgb = torch.zeros((ray_dirs.shape[0], 3), device=self.device)
         if idx.numel() == 0:
             return rgb, hit, t
-        _, grad = self.sdf_net.value_and_grad(xc[idx], ratio, want_feat=True)
+        sdf_ratio = ratio.get("sdfRatio") if isinstance(ratio, dict) else ratio
+        _, grad = self.sdf_net.value_and_grad(xc[idx], sdf_ratio, want_feat=True)
         n = torch.nn.functional.normalize(grad, dim=1)
         with torch.no_grad():
             col = render_net(xc[idx], n, ray_dirs[idx], self.sdf_net.rendcond,
-                             {"renderRatio": None if ratio is None else ratio.get("renderRatio")})
+                             {"renderRatio": ratio.get("renderRatio") if isinstance(ratio, dict) else ratio})
         rgb.index_copy_(0, idx, col)
         return rgb, hit, t
