@@ -146,6 +146,22 @@ RECMV_API int recmv_sdf_mlp_fwd_grad(const float* x, const void* packed, const f
                            float* out_sdf, float* out_feat, float* out_grad, int64_t P, int mode,
                            recmv_stream_t stream);
 
+/* ---- A4 + A5: MLPTranslator.forward followed by LBSkinner.forward (CompositeDeformer) in ONE launch ------
+ * replaces model/Deformer.py:171-206 (PE ++ cond[batch] -> 512 x4 ReLU -> 3, p + offset) and :406-445.
+ * Same tcgen05 engine as the SDF network (3 input K blocks, 4 hidden layers, 32-wide tail tile).
+ * pack: W_l [out,in] row-major fp32, l = 0..4 concatenated (167->512, 512->512 x3, 512->3); b likewise.
+ * conds [F,128]; batch_inds [P] i64 or NULL (frame = p / points_per_frame); pe_w [12] host.
+ * Outputs (each may be NULL): out_translated = p + offset, out_offset, out_posed = LBS(p + offset) (needs
+ * A [F,24,4,4], trans [F,3] (+extra_trans) and the channels-last voxel).  TC modes only.                   */
+RECMV_API size_t recmv_translator_packed_bytes(void);
+RECMV_API int recmv_translator_pack_weights(const float* W_all, const float* b_all, void* packed,
+                                  recmv_stream_t stream);
+RECMV_API int recmv_deformer_fwd(const float* ps, const float* conds, const int64_t* batch_inds,
+                       int64_t points_per_frame, int num_frames, const void* packed,
+                       const float* pe_w /*host*/, const float* A, const float* trans,
+                       const recmv_voxel_t* vox /*host, may be NULL*/, float* out_translated,
+                       float* out_offset, float* out_posed, int64_t P, int mode, recmv_stream_t stream);
+
 /* Non-blocking health check of the tcgen05 path on the current device: every mbarrier wait in the kernel is
  * bounded; a wait that times out records {code, barrier tag, block} in mapped host memory and later launches
  * are refused with RECMV_E_DEVICE.  info may be NULL; clear != 0 resets the record.                        */

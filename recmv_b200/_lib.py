@@ -62,6 +62,11 @@ SIGNATURES = {
                                   c_int, c_void_p]),
     "recmv_sdf_mlp_fwd_grad": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_void_p, c_int64,
                                        c_int, c_void_p]),
+    "recmv_translator_packed_bytes": (c_size_t, []),
+    "recmv_translator_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "recmv_deformer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, POINTER(c_float),
+                                   c_void_p, c_void_p, POINTER(Voxel), c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_int, c_void_p]),
     "recmv_check_async_errors": (c_int, [POINTER(c_int), c_int]),
     "recmv_sdf_mlp_tc_debug": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int64,
                                        c_int, c_int, c_void_p, POINTER(c_int), c_void_p, c_void_p]),

@@ -74,6 +74,17 @@ struct TcParams {
   unsigned long long* trace;
   // forward-mode (JVP) variant: out_grad [P,3] = d sdf / d x; each point occupies 4 adjacent tile rows
   float* out_grad;
+  // deformer network (kNet == 1): MLPTranslator 167 -> 512 x4 -> 3 (ReLU) followed by LBS forward
+  const float* conds;            // [F,128]
+  const long long* batch_inds;   // [P] or NULL (frame = p / points_per_frame)
+  long long points_per_frame;
+  int num_frames;
+  const float* bones;            // A [F,24,4,4] (NULL: translator only)
+  const float* trans;            // [F,3]
+  Voxel vox;
+  float* out_translated;         // [P,3]  p + delta
+  float* out_offset;             // [P,3]  delta (MLPTranslator.offset), optional
+  float* out_posed;              // [P,3]  LBS(p + delta), optional
 };
 #define TRACE(role, it, l, ev)                                                                     \
   do {                                                                                             \
@@ -113,11 +124,37 @@ __device__ __forceinline__ float act_jvp(float z_own, float z_val, bool is_value
   return is_value ? sp : z_own * sig;
 }
 
+// Network descriptions driving the same pipeline.
+template <int kNet> struct Net;
+// SDF network (model/network.py:135-141): PE block -> 512 x3 -> 473 -> [skip: +PE block] 512 x4 -> 257
+template <> struct Net<0> {
+  static constexpr int kLayers = 9, kPanels = kNumPanels, kInFreeLayer = 4;
+  __device__ static int nkb(int l) { return num_panels(l); }
+  __device__ static int pbase(int l) { return panel_base(l); }
+  __device__ static int kb_at(int l, int i) { return kb_order(l, i); }
+  __device__ static bool is_pe(int l, int kbi) { return l == 0 || (l == 4 && kbi == 8); }
+  __device__ static int ntiles(int) { return 2; }
+  __device__ static bool small(int l, int nt) { return l == 8 && nt == 1; }
+};
+// MLPTranslator (model/Deformer.py:141-206): [PE(39) | cond(128) | 0 x25] = 3 K blocks -> 512 x4 (ReLU) -> 3
+template <> struct Net<1> {
+  static constexpr int kLayers = 5, kPanels = 35, kInFreeLayer = 4;
+  __device__ static int nkb(int l) { return l == 0 ? 3 : 8; }
+  __device__ static int pbase(int l) { return l == 0 ? 0 : 3 + 8 * (l - 1); }
+  __device__ static int kb_at(int l, int i) { return l == 0 ? i : ((i & 4) | ((i & 1) << 1) | ((i >> 1) & 1)); }
+  __device__ static bool is_pe(int, int) { return false; }   // the input block lives in the activation buffer
+  __device__ static int ntiles(int l) { return l == 4 ? 1 : 2; }
+  __device__ static bool small(int l, int) { return l == 4; }
+};
+
 }  // namespace
 
-template <bool kJvp>
+template <bool kJvp, int kNet>
 __global__ void __cluster_dims__(2 * kPairs, 1, 1) __launch_bounds__(kThreads, 1)
 sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
+  using NetT = Net<kNet>;
+  constexpr int kNumLayers = NetT::kLayers;   // shadows the SDF constant of common.cuh
+  static_assert(!kJvp || kNet == 0, "the forward-mode variant exists for the SDF network");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -170,20 +207,20 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
       for (int g = 0; g < kPairs; ++g) mask |= (uint16_t)(1u << (2 * g + (int)rank));
       for (long long it = 0; it < n_iter; ++it) {
         for (int l = 0; l < kNumLayers; ++l) {
-          const int nkb = num_panels(l);
+          const int nkb = NetT::nkb(l);
           TRACE(3, it, l, 0);
           // last layer, parity mode: sweep 0 streams (w_hi, w_lo) for the correction MMAs, sweep 1 streams
           // w_hi again for the hi*hi MMAs (see the MMA issuer)
           const int nsweep = (passes == 3 && l == kNumLayers - 1) ? 2 : 1;
           for (int sweep = 0; sweep < nsweep; ++sweep) {
             for (int i = 0; i < nkb; ++i) {
-              const int kbi = kb_order(l, i);
+              const int kbi = NetT::kb_at(l, i);
               if (i == nkb - 1) TRACE(3, it, l, 1);
-              for (int nt = 0; nt < 2; ++nt) {
+              for (int nt = 0; nt < NetT::ntiles(l); ++nt) {
                 const int nplanes = (passes == 3 && sweep == 0) ? 2 : 1;
                 for (int plane = 0; plane < nplanes; ++plane) {
                   mbar_wait(BAR(kBarEmpty + slot), ring ^ 1u, abort_flag, prm.status, 100 + slot);
-                  const int row = (plane * kNumPanels + panel_base(l) + kbi) * 512 + nt * 256 + (int)rank * 128;
+                  const int row = (plane * NetT::kPanels + NetT::pbase(l) + kbi) * 512 + nt * 256 + (int)rank * 128;
                   tma_load_2d_pair_mcast(base + kOffW + slot * kSlotBytes, (const void*)&tmap128,
                                          mapa(BAR(kBarFull + slot), 0), mask, 0, row);
                   if (++slot == kSlots) { slot = 0; ring ^= 1u; }
@@ -209,7 +246,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           mbar_wait(BAR(kBarAccEmpty + buf), (use & 1u) ^ 1u, abort_flag, prm.status, 200 + buf);
           tc_fence_after();
           TRACE(0, it, l, 1);
-          const int nkb = num_panels(l);
+          const int nkb = NetT::nkb(l);
           // Ordering for accuracy (parity mode, last layer): the tensor core accumulates with truncation, so
           // every MMA added to a LARGE accumulator costs ~1 ulp of it.  The correction products (lo*hi,
           // hi*lo) are 2^-11 of the result: issued first, while the accumulator is still tiny, their
@@ -218,11 +255,13 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           const bool two_sweeps = (passes == 3 && l == kNumLayers - 1);
           for (int sweep = 0; sweep < (two_sweeps ? 2 : 1); ++sweep) {
             for (int i = 0; i < nkb; ++i) {
-              const int kbi = kb_order(l, i);
-              const bool is_pe = (l == 0) || (l == 4 && kbi == 8);
+              const int kbi = NetT::kb_at(l, i);
+              const bool is_pe = NetT::is_pe(l, kbi);
               if (sweep == 0) {
+                // layer 0 consumes what the prologue wrote (PE buffer, or the input K blocks of the deformer);
+                // every other layer the K blocks released by the previous layer's epilogue
                 if (l == 0) mbar_wait(BAR(kBarPeReady), (uint32_t)(it & 1), abort_flag, prm.status, 210);
-                if (!is_pe) mbar_wait(BAR(kBarAReady + kbi), (uint32_t)((l - 1) & 1), abort_flag, prm.status, 220 + kbi);
+                else if (!is_pe) mbar_wait(BAR(kBarAReady + kbi), (uint32_t)((l - 1) & 1), abort_flag, prm.status, 220 + kbi);
                 tc_fence_after();
                 if (i == 0) TRACE(0, it, l, 2);
                 if (i == 4) TRACE(0, it, l, 3);
@@ -230,8 +269,8 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
               }
               const uint64_t a_hi = smem_desc_sw128(is_pe ? base + kOffPeHi : base + kOffAHi + kbi * 8192);
               const uint64_t a_lo = smem_desc_sw128(is_pe ? base + kOffPeLo : base + kOffALo + kbi * 8192);
-              for (int nt = 0; nt < 2; ++nt) {
-                const bool small = (l == 8 && nt == 1);
+              for (int nt = 0; nt < NetT::ntiles(l); ++nt) {
+                const bool small = NetT::small(l, nt);
                 const uint32_t idesc = small ? idesc_f16(128, 32) : idesc_f16(128, 256);
                 const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + nt * 128);
                 // ---- slot with w_hi -------------------------------------------------------------------
@@ -271,7 +310,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           }
           umma_commit_pair(BAR(kBarAccFull + buf), pair_mask);
           TRACE(0, it, l, 5);
-          if (l == 4) umma_commit_pair(BAR(kBarPeFree), pair_mask);
+          if (l == NetT::kInFreeLayer) umma_commit_pair(BAR(kBarPeFree), pair_mask);  // prologue may refill its block
         }
       }
     }
@@ -297,21 +336,21 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         tc_fence_after();
         if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 1);
         const float* bias = prm.bias + l * 512;
-        for (int nt = 0; nt < 2; ++nt) {
-          const bool small = (l == 8 && nt == 1);
+        for (int nt = 0; nt < NetT::ntiles(l); ++nt) {
+          const bool small = NetT::small(l, nt);
           if (small && grp != 0) continue;  // the 32-wide tail tile has a single 16-column group per half
           for (int cc = 0; cc < (small ? 32 : 64); cc += 32) {
             const int c0 = small ? cc : cc * 2 + grp * 32;  // K block (cc/32) of this half, 32-column part grp
             uint32_t r[32];
             tmem_ld32(tmem_base + lane_addr + (uint32_t)(buf * 256 + nt * 128 + c0), r);
             tmem_ld_wait();
-            const int f0 = small ? 256 + half * 16 + c0 : nt * 256 + half * 128 + c0;
+            const int f0 = small ? nt * 256 + half * 16 + c0 : nt * 256 + half * 128 + c0;
             if (prm.dbg_out && prm.dbg_layer == l && tile == 0 && !small) {  // cluster 0, pair 0
               float* d = prm.dbg_out + ((size_t)rank * kRowsPerCta + row) * 512 + f0;
 #pragma unroll
               for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(r[c]) * kAccUnscale;
             }
-            if (l < 8) {
+            if (l < kNumLayers - 1) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int f = f0 + 8 * j;
@@ -328,9 +367,12 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                     const float z_val = __shfl_sync(0xffffffffu, z_own, lane & ~3);  // the point's value row
                     v[e] = act_jvp(z_own, z_val, is_value) * kActScale;
                   }
-                } else {
+                } else if (kNet == 0) {
 #pragma unroll
                   for (int e = 0; e < 8; ++e) v[e] = softplus100_fast(v[e]) * kActScale;
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f) * kActScale;   // ReLU
                 }
                 uint4 hi, lo;
                 split8(v, hi, lo);
@@ -344,6 +386,28 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(BAR(kBarAReady + (f0 >> 6)), lrank);
                 if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 2 + nt);
+              }
+            } else if (kNet == 1) {
+              // deformer: columns 0..2 of the tail tile = offset; out = p + offset, then LBS forward
+              if (p < prm.P && half == 0 && c0 == 0) {
+                const float dx = fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias + 0));
+                const float dy = fmaf(__uint_as_float(r[1]), kAccUnscale, __ldg(bias + 1));
+                const float dz = fmaf(__uint_as_float(r[2]), kAccUnscale, __ldg(bias + 2));
+                const float x = __ldg(prm.src.x + 3 * p), y = __ldg(prm.src.x + 3 * p + 1), z = __ldg(prm.src.x + 3 * p + 2);
+                const float tx = x + dx, ty = y + dy, tz = z + dz;
+                if (prm.out_translated) { prm.out_translated[3 * p] = tx; prm.out_translated[3 * p + 1] = ty; prm.out_translated[3 * p + 2] = tz; }
+                if (prm.out_offset) { prm.out_offset[3 * p] = dx; prm.out_offset[3 * p + 1] = dy; prm.out_offset[3 * p + 2] = dz; }
+                if (prm.out_posed) {
+                  long long f = prm.batch_inds ? prm.batch_inds[p] : (prm.points_per_frame > 0 ? p / prm.points_per_frame : 0);
+                  f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
+                  float w[24], T[12];
+                  sample_skin24(prm.vox, tx, ty, tz, w);
+                  blend_bones(prm.bones + (size_t)f * 384, w, T);
+                  const float* tr = prm.trans + 3 * f;
+                  prm.out_posed[3 * p + 0] = (T[0] * tx + T[1] * ty + T[2] * tz + T[3]) + __ldg(tr + 0);
+                  prm.out_posed[3 * p + 1] = (T[4] * tx + T[5] * ty + T[6] * tz + T[7]) + __ldg(tr + 1);
+                  prm.out_posed[3 * p + 2] = (T[8] * tx + T[9] * ty + T[10] * tz + T[11]) + __ldg(tr + 2);
+                }
               }
             } else if (p < prm.P) {
               // last layer: column 0 = sdf, columns 1..256 = features
@@ -378,8 +442,38 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
       const long long tile = tile_of(it);
       const long long p = kJvp ? tile * 32 + (long long)rank * 16 + (row >> 2)
                                : tile * 128 + (long long)rank * kRowsPerCta + row;
-      float pe[40];
       bool ok = true;
+      if (kNet == 1) {
+        // deformer input row: [PE(p) (39) | cond[frame] (128) | 0 (25)] = three 64-wide K blocks written into the
+        // activation buffer itself (free again once the previous tile's last layer has been issued and done)
+        float in[192];
+#pragma unroll
+        for (int e = 0; e < 192; ++e) in[e] = 0.f;
+        if (p < prm.P) {
+          const float x = __ldg(prm.src.x + 3 * p), y = __ldg(prm.src.x + 3 * p + 1), z = __ldg(prm.src.x + 3 * p + 2);
+          positional_encode(x, y, z, prm.pw.w, in);
+          long long f = prm.batch_inds ? prm.batch_inds[p] : (prm.points_per_frame > 0 ? p / prm.points_per_frame : 0);
+          f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
+          const float4* c = reinterpret_cast<const float4*>(prm.conds + (size_t)f * 128);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float4 t = __ldg(c + e);
+            in[39 + 4 * e] = t.x; in[40 + 4 * e] = t.y; in[41 + 4 * e] = t.z; in[42 + 4 * e] = t.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 167; ++e) in[e] *= kActScale;
+        }
+        if (it > 0) mbar_wait(BAR(kBarPeFree), (uint32_t)((it - 1) & 1), abort_flag, prm.status, 400);
+#pragma unroll
+        for (int chunk = 0; chunk < 24; ++chunk) {
+          uint4 hi, lo;
+          split8(in + 8 * chunk, hi, lo);
+          const uint32_t off = (uint32_t)(chunk >> 3) * 8192u + sw128_offset(row, chunk & 7);
+          st_shared_v4(base + kOffAHi + off, hi);
+          st_shared_v4(base + kOffALo + off, lo);
+        }
+      } else {
+      float pe[40];
       if (p < prm.P) {
         float cx, cy, cz;
         ok = fetch_point(prm.src, p, cx, cy, cz);
@@ -419,6 +513,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         st_shared_v4(base + kOffPeHi + off, hi);
         st_shared_v4(base + kOffPeLo + off, lo);
       }
+      }
       valid[(it & 1) * 64 + row] = ok ? 1 : 0;
       fence_proxy_async();
       __syncwarp();
@@ -449,11 +544,43 @@ int tc_status_record(int dev, DevStatus** out) {
   return 0;
 }
 
-struct TmapCache {
+struct TmapCacheEntry {
   const void* base = nullptr;
   CUtensorMap m128;
-  int max_clusters = 0;
 };
+using TmapCache = TmapCacheEntry;
+
+// opt-in to the 226 KB of dynamic shared memory once per device for every instantiation
+int tc_prepare_launch(int dev) {
+  static bool done[16] = {false};
+  if (done[dev & 15]) return 0;
+  cudaError_t e = cudaFuncSetAttribute(sdf_tc_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  done[dev & 15] = true;
+  return 0;
+}
+
+// clusters must fit inside a GPC: ask the driver how many are co-resident and run exactly that many
+// (persistent kernel; a second wave would double the time)
+int tc_max_clusters(int dev) {
+  static int cached[16] = {0};
+  if (cached[dev & 15]) return cached[dev & 15];
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_sms() / (2 * kPairs) * (2 * kPairs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2 * kPairs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sdf_tc_kernel<false, 0>, &cfg);
+  if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / (2 * kPairs) - 4; }
+  cached[dev & 15] = n;
+  return n;
+}
 }  // namespace
 
 static int launch_tc(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
@@ -472,14 +599,8 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
     if (s) return s;
     tc_.base = panels;
   }
-  static bool attr_done[16] = {false};
-  if (!attr_done[dev & 15]) {
-    cudaError_t e = cudaFuncSetAttribute(sdf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(sdf_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    attr_done[dev & 15] = true;
-  }
+  int sp = tc_prepare_launch(dev);
+  if (sp) return sp;
   // Device status record in MAPPED pinned host memory: a bounded wait that times out writes it there, the
   // host sees it without a synchronisation and refuses further work (recmv_check_async_errors()).
   DevStatus* sd = nullptr;
@@ -491,30 +612,15 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   prm.bias = (const float*)(pb + L.bias_all_off);
   prm.out_sdf = out_sdf; prm.out_feat = out_feat; prm.P = P; prm.passes = passes; prm.status = sd;
   prm.dbg_layer = dbg_layer; prm.dbg_out = dbg_out; prm.trace = trace; prm.out_grad = out_grad;
-  if (tc_.max_clusters == 0) {
-    // clusters must fit inside a GPC: ask the driver how many 4-CTA clusters are co-resident and run
-    // exactly that many (persistent kernel; a second wave would double the time)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(num_sms() / (2 * kPairs) * (2 * kPairs));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2 * kPairs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sdf_tc_kernel<false>, &cfg);
-    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / (2 * kPairs) - 4; }
-    tc_.max_clusters = n;
-  }
   const int pts_per_tile = out_grad ? 32 : 128;
   int64_t tiles = (P + pts_per_tile - 1) / pts_per_tile;
   int64_t want = (tiles + kPairs - 1) / kPairs;
-  int clusters = (int)(want < tc_.max_clusters ? want : tc_.max_clusters);
+  const int maxc = tc_max_clusters(dev);
+  int clusters = (int)(want < maxc ? want : maxc);
   if (out_grad)
-    sdf_tc_kernel<true><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
+    sdf_tc_kernel<true, 0><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
   else
-    sdf_tc_kernel<false><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
+    sdf_tc_kernel<false, 0><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
   int s = launch_status();
   if (s) return s;
   if (status_host) {  // diagnostics path: wait for the launch, then report (and clear) the status record
@@ -542,6 +648,109 @@ int tc_sdf_forward_grad(const float* x, const void* packed, const PeWeights& pw,
 }  // namespace recmv
 
 using namespace recmv;
+
+// ---------------------------------------------------------------------------------------------------------
+// Deformer network: MLPTranslator (model/Deformer.py:141-206) + LBSkinner.forward (Deformer.py:406-445)
+// ---------------------------------------------------------------------------------------------------------
+namespace recmv {
+namespace {
+constexpr int kDefLayers = 5, kDefPanels = 35;
+constexpr int def_in(int l) { return l == 0 ? 167 : 512; }
+constexpr int def_out(int l) { return l == 4 ? 3 : 512; }
+constexpr int def_pbase(int l) { return l == 0 ? 0 : 3 + 8 * (l - 1); }
+constexpr int def_npanels(int l) { return l == 0 ? 3 : 8; }
+struct DeformLayout { size_t bias_off, f16_off, total; };
+DeformLayout deform_layout() {
+  DeformLayout L;
+  L.bias_off = 0;
+  L.f16_off = ((size_t)kDefLayers * 512 * 4 + 1023) & ~(size_t)1023;
+  L.total = L.f16_off + (size_t)2 * kDefPanels * 512 * 64 * 2;
+  return L;
+}
+
+__global__ void __launch_bounds__(256) pack_plain_layer_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                                               int out, int in, int pbase, int npanels,
+                                                               float* __restrict__ bpad, __half* __restrict__ planes,
+                                                               int total_panels) {
+  int64_t total = (int64_t)npanels * 512 * 64;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pi = (int)(i / (512 * 64)), n = (int)((i / 64) % 512), kk = (int)(i % 64);
+    const int k = pi * 64 + kk;
+    const float v = (n < out && k < in) ? W[(size_t)n * in + k] * kWgtScale : 0.f;
+    const __half h = __float2half_rn(v);
+    const size_t o = ((size_t)(pbase + pi) * 512 + n) * 64 + kk;
+    planes[o] = h;
+    planes[(size_t)total_panels * 512 * 64 + o] = __float2half_rn(v - __half2float(h));
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 512; i += gridDim.x * blockDim.x) bpad[i] = i < out ? b[i] : 0.f;
+}
+TmapCacheEntry g_def_tmap[16];
+}  // namespace
+}  // namespace recmv
+
+extern "C" size_t recmv_translator_packed_bytes(void) { return deform_layout().total; }
+
+extern "C" int recmv_translator_pack_weights(const float* W_all, const float* b_all, void* packed,
+                                             recmv_stream_t stream) {
+  if (!W_all || !b_all || !packed) return RECMV_E_NULL;
+  if (((uintptr_t)packed & 1023) != 0) return RECMV_E_SHAPE;
+  DeformLayout L = deform_layout();
+  char* base = (char*)packed;
+  size_t woff = 0, boff = 0;
+  for (int l = 0; l < kDefLayers; ++l) {
+    pack_plain_layer_kernel<<<stride_grid((int64_t)def_npanels(l) * 512 * 64, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+        W_all + woff, b_all + boff, def_out(l), def_in(l), def_pbase(l), def_npanels(l),
+        (float*)(base + L.bias_off) + l * 512, (__half*)(base + L.f16_off), kDefPanels);
+    int s = launch_status();
+    if (s) return s;
+    woff += (size_t)def_in(l) * def_out(l);
+    boff += def_out(l);
+  }
+  return RECMV_OK;
+}
+
+extern "C" int recmv_deformer_fwd(const float* ps, const float* conds, const int64_t* batch_inds,
+                                  int64_t points_per_frame, int num_frames, const void* packed, const float* pe_w,
+                                  const float* A, const float* trans, const recmv_voxel_t* vox, float* out_translated,
+                                  float* out_offset, float* out_posed, int64_t P, int mode, recmv_stream_t stream) {
+  if (P < 0 || num_frames <= 0) return RECMV_E_SHAPE;
+  if (P == 0) return RECMV_OK;
+  if (!ps || !conds || !packed || !pe_w) return RECMV_E_NULL;
+  if (out_posed && (!A || !trans || !vox || !vox->ws_cl)) return RECMV_E_NULL;
+  if (mode != RECMV_MLP_TC_F16X3 && mode != RECMV_MLP_TC_F16X1) return RECMV_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DeformLayout L = deform_layout();
+  const char* pb = (const char*)packed;
+  TmapCacheEntry& tc_ = g_def_tmap[dev & 15];
+  if (tc_.base != pb + L.f16_off) {
+    int s = make_panel_tmap(&tc_.m128, pb + L.f16_off, (uint64_t)2 * kDefPanels * 512, 128);
+    if (s) return s;
+    tc_.base = pb + L.f16_off;
+  }
+  int s0 = tc_prepare_launch(dev);
+  if (s0) return s0;
+  DevStatus* sd = nullptr;
+  s0 = tc_status_record(dev, &sd);
+  if (s0) return s0;
+  if (sd->code != 0) return RECMV_E_DEVICE;
+  TcParams prm = {};
+  prm.src.x = ps; prm.src.S = 1;
+  for (int i = 0; i < 12; ++i) prm.pw.w[i] = pe_w[i];
+  prm.bias = (const float*)(pb + L.bias_off);
+  prm.P = P; prm.passes = mode == RECMV_MLP_TC_F16X3 ? 3 : 1; prm.status = sd; prm.dbg_layer = -1;
+  prm.conds = conds; prm.batch_inds = (const long long*)batch_inds; prm.points_per_frame = points_per_frame;
+  prm.num_frames = num_frames; prm.bones = A; prm.trans = trans;
+  if (vox) prm.vox = to_voxel(vox);
+  prm.out_translated = out_translated; prm.out_offset = out_offset; prm.out_posed = out_posed;
+  int64_t tiles = (P + 127) / 128;
+  int64_t want = (tiles + kPairs - 1) / kPairs;
+  int maxc = tc_max_clusters(dev);
+  int clusters = (int)(want < maxc ? want : maxc);
+  sdf_tc_kernel<false, 1><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
+  return launch_status();
+}
 
 // Reports (without synchronising) whether any tcgen05 launch on the current device has aborted on a bounded
 // wait since the last check: 0 = none, RECMV_E_DEVICE otherwise; info[3] = {code, barrier tag, block}.

@@ -51,10 +51,38 @@ class CompositeDeformer(nn.Module):
 
     def forward(self, ps, conds, batch_inds=None, **kwargs):
         assert (self.N == len(conds))
+        fused = self._fused_forward(ps, conds, batch_inds, kwargs)
+        if fused is not None:
+            return fused
         out = ps
         for cond, deformer in zip(conds, self.defs):
             out = deformer(out, cond, batch_inds, **kwargs)
         return out
+
+    def _fused_forward(self, ps, conds, batch_inds, kwargs):
+        """[MLPTranslator, LBSkinner] without an autograd graph -> ONE launch (translator MLP on tcgen05, then
+        the skinning-voxel sample + bone blend in the same kernel's epilogue)."""
+        if self.N != 2 or not isinstance(self.defs[0], MLPTranslator) or not isinstance(self.defs[1], LBSkinner):
+            return None
+        tr, sk = self.defs[0], self.defs[1]
+        if type(ps) == list or not ps.is_cuda or not tr.fusable or tr.mlp_mode == ops.MLP_FP32_SIMT:
+            return None
+        poses, trans = conds[1]
+        tensors = [ps, conds[0], poses, trans] + list(tr.parameters())
+        if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+            return None
+        A = sk.bone_matrices(poses)
+        center = sk.bbox_center.view(-1)[:3].tolist()
+        extend = float(sk.bbox_extend.view(-1)[0])
+        ratio = kwargs['ratio']['deformerRatio']
+        ppf = 0 if batch_inds is not None else ps.shape[1]
+        _, off, posed = ops.deformer_forward(ps.reshape(-1, 3), conds[0], tr.packed_weights(),
+                                             ratio_to_weights(tr.multires, ratio), batch_inds, ppf,
+                                             (A, trans + sk.extra_trans, sk.ws_channels_last(), center, extend),
+                                             tr.mlp_mode, want_offset=True, want_translated=False)
+        tr.offset[kwargs['offset_type']] = off if batch_inds is not None else off.view(ps.shape[0], ps.shape[1], 3)
+        tr.last_path = sk.last_path = "fused-deformer"
+        return posed if batch_inds is not None else posed.view(ps.shape)
 
 
 class MLPTranslator(nn.Module):

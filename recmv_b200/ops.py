@@ -367,6 +367,61 @@ def sdf_value_and_grad(x, packed, pe_w=None, mode=None, want_feat=False):
     return sdf, grad, feat
 
 
+TRANSLATOR_LAYER_SHAPES = [(512, 167), (512, 512), (512, 512), (512, 512), (3, 512)]
+
+
+def _aligned_blob(nbytes, dev):
+    raw = torch.empty((nbytes + 1024,), dtype=torch.uint8, device=dev)
+    off = (-raw.data_ptr()) % 1024
+    blob = raw[off:off + nbytes]
+    blob._keepalive = raw
+    return blob
+
+
+def translator_pack_weights(Ws, bs):
+    """MLPTranslator weights (lin0..lin4, no weight-norm) -> packed fp16 hi/lo panels for the tcgen05 engine."""
+    dev = Ws[0].device
+    for (o, i), W, b in zip(TRANSLATOR_LAYER_SHAPES, Ws, bs):
+        if tuple(W.shape) != (o, i) or tuple(b.shape) != (o,):
+            raise RuntimeError(f"unexpected translator layer shape {tuple(W.shape)} (want {(o, i)})")
+    W_all = torch.cat([W.detach().reshape(-1).float() for W in Ws]).contiguous()
+    b_all = torch.cat([b.detach().reshape(-1).float() for b in bs]).contiguous()
+    lib = _lib.load()
+    packed = _aligned_blob(lib.recmv_translator_packed_bytes(), dev)
+    with torch.cuda.device(dev):
+        check(lib.recmv_translator_pack_weights(_ptr(W_all), _ptr(b_all), _ptr(packed), _stream(W_all)),
+              "recmv_translator_pack_weights")
+    return packed
+
+
+def deformer_forward(ps, conds, packed, pe_w, batch_inds=None, points_per_frame=0, skin=None, mode=None,
+                     want_offset=True, want_translated=True):
+    """MLPTranslator (+ LBS forward when skin = (A, trans, ws_cl, center, extend)) in one fused launch.
+    Returns (translated [P,3] or None, offset [P,3] or None, posed [P,3] or None)."""
+    mode = DEFAULT_MLP_MODE if mode is None else mode
+    ps = ps.contiguous().float()
+    _check_input(ps, "ps")
+    conds = conds.contiguous().float()
+    P = ps.shape[0]
+    dev = ps.device
+    tr = torch.empty((P, 3), dtype=torch.float32, device=dev) if want_translated else None
+    off = torch.empty((P, 3), dtype=torch.float32, device=dev) if want_offset else None
+    posed, A, trans, vox = None, None, None, None
+    if skin is not None:
+        A, trans, ws_cl, center, extend = skin
+        A, trans = A.contiguous().float(), trans.contiguous().float()
+        vox = byref(make_voxel(ws_cl, center, extend))
+        posed = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    if batch_inds is not None:
+        batch_inds = batch_inds.contiguous().long()
+    with torch.cuda.device(dev):
+        check(_lib.load().recmv_deformer_fwd(_ptr(ps), _ptr(conds), _ptr(batch_inds), int(points_per_frame),
+                                             int(conds.shape[0]), _ptr(packed), _pe_array(pe_w), _ptr(A), _ptr(trans),
+                                             vox, _ptr(tr), _ptr(off), _ptr(posed), P, mode, _stream(ps)),
+              "recmv_deformer_fwd")
+    return tr, off, posed
+
+
 def make_raymarch(cam_pos, t_near, t_far, samples):
     rm = RayMarch()
     rm.cam_pos = (c_float * 3)(*[float(c) for c in cam_pos])

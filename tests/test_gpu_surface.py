@@ -100,3 +100,38 @@ def test_c2f_sweep_and_discretize_on_gpu():
     with torch.no_grad():
         assert sdf(v, None).abs().max() < 2e-3       # vertices sit on the zero level set (cell size 0.0155)
     assert sum(s[3] for s in eng2.stats) < 0.25 * 129 ** 3
+
+
+def test_fused_translator_and_deformer_match_reference():
+    """A4 / A5: MLPTranslator alone (golden from the reference class) and the CompositeDeformer = translator +
+    LBS in one launch (golden `ds` from the reference CompositeDeformer)."""
+    g = load_golden("translator.npz")
+    torch.manual_seed(1)
+    tr = M.MLPTranslator(128, 6)
+    from recmv_b200 import testing
+    testing.perturb_module(tr, 202, scale=0.5)
+    tr = tr.to(DEV)
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in g.items() if k not in ("param_names", "param_sums")}
+    with torch.no_grad():
+        out = tr(t["p"], t["conds"], t["batch_inds"], ratio={"deformerRatio": 0.6}, offset_type="body")
+    assert tr.last_path == "fused"
+    print(f"translator: out {norm_err(out, t['out']):.2e} offset {norm_err(tr.offset['body'], t['offset']):.2e}")
+    assert norm_err(out, t["out"]) < 1e-4 and norm_err(tr.offset["body"], t["offset"]) < 2e-4
+    with torch.no_grad():   # [N,V,3] call form
+        out2 = tr(t["p"][:1500].view(3, 500, 3), t["conds"], None, ratio={"deformerRatio": 0.6}, offset_type="b2")
+    ref2 = None
+    tr.mlp_mode = _lib.MLP_FP32_SIMT   # explicit composite path for comparison
+    with torch.no_grad():
+        ref2 = tr(t["p"][:1500].view(3, 500, 3), t["conds"], None, ratio={"deformerRatio": 0.6}, offset_type="b3")
+    assert tr.last_path == "autograd-composite" and norm_err(out2, ref2) < 1e-4
+    # composite deformer
+    gs = load_golden("surface.npz")
+    ts = {k: torch.from_numpy(v).to(DEV) for k, v in gs.items()}
+    sdf, deformer = _scene()
+    with torch.no_grad():
+        ds = deformer(ts["ps"], [ts["conds"], [ts["poses"], ts["trans"]]], ts["batch_inds"], ratio=RATIO,
+                      offset_type="body")
+    assert deformer.defs[0].last_path == "fused-deformer"
+    print(f"composite deformer: {norm_err(ds, ts['ds']):.2e}")
+    assert norm_err(ds, ts["ds"]) < 1e-4
+    ops.check_async_errors()
