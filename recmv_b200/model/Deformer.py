@@ -107,10 +107,38 @@ class MLPTranslator(nn.Module):
             setattr(self, "lin" + str(l), lin)
         self.relu = nn.ReLU()
         self.offset = {}
+        self.mlp_mode = None
+        self.last_path = None
+        self._packed, self._packed_key = None, None
+        self.fusable = (multires == 6 and feature_vector_size == 128 and not weight_norm)
+
+    def packed_weights(self):
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or key != self._packed_key:
+            with torch.no_grad():
+                self._packed = ops.translator_pack_weights([getattr(self, "lin%d" % l).weight for l in range(5)],
+                                                           [getattr(self, "lin%d" % l).bias for l in range(5)])
+            self._packed_key = key
+        return self._packed
 
     def forward(self, ps, conds, batch_inds=None, **kwargs):
         ratio = kwargs['ratio']['deformerRatio']
         offset_type = kwargs['offset_type']
+        needs_graph = torch.is_grad_enabled() and (ps.requires_grad or conds.requires_grad
+                                                   or any(p.requires_grad for p in self.parameters()))
+        if self.fusable and ps.is_cuda and not needs_graph and self.mlp_mode != ops.MLP_FP32_SIMT:
+            self.last_path = "fused"
+            ppf = 0 if batch_inds is not None else ps.shape[1]
+            tr, off, _ = ops.deformer_forward(ps.reshape(-1, 3), conds, self.packed_weights(),
+                                              ratio_to_weights(self.multires, ratio), batch_inds, ppf, None,
+                                              self.mlp_mode)
+            if batch_inds is not None:
+                self.offset[offset_type] = off
+                return tr
+            self.offset[offset_type] = off.view(ps.shape[0], ps.shape[1], 3)
+            return tr.view(ps.shape[0], ps.shape[1], 3)
+        self.last_path = "autograd-composite"
         if self.embed_fn is not None:
             ps = self.embed_fn(ps, ratio_to_weights(self.multires, ratio))
         if batch_inds is not None:
