@@ -177,6 +177,10 @@ RECMV_API int recmv_sdf_mlp_tc_debug(const float* x, const void* packed, const f
                            unsigned long long* trace /*device [4][2][9][16] clock stamps or NULL*/,
                            recmv_stream_t stream);
 
+/* Diagnostics: tcgen05 issue-rate microbenchmark (cycles per M x N x 16 kind::f16 MMA with smem operands). */
+RECMV_API int recmv_tc_microbench(int cta_group, int M, int N, int iters, int num_ctas, int flags, const void* gsrc,
+                        unsigned long long* out, recmv_stream_t stream);
+
 /* ---- the fused render path (BASELINE north star) -------------------------------------------------
  * One launch: ray r, sample k -> x_obs = cam_pos + t_k dir_r, t_k = t_near + (k+1/2)(t_far-t_near)/S
  * -> inverse LBS (frame = frame_of_ray[r] or r / rays_per_frame) -> PE -> SDF MLP -> sdf [R,S].

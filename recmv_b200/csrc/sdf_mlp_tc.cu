@@ -184,8 +184,8 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
     for (int s = 0; s < kSlots; ++s) { mbar_init(BAR(kBarFull + s), 1); mbar_init(BAR(kBarEmpty + s), kPairs); }
     for (int k = 0; k < 8; ++k) mbar_init(BAR(kBarAReady + k), 8);
     mbar_init(BAR(kBarPeReady), 4);
-    mbar_init(BAR(kBarPeFree), 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 1); mbar_init(BAR(kBarAccEmpty + b), 2 * kEpiWarps); }
+    mbar_init(BAR(kBarPeFree), 2);                               // one commit per MMA issuer
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 2); mbar_init(BAR(kBarAccEmpty + b), 2 * kEpiWarps); }
     // arm generation 0 of every weight slot of this pair (both CTAs' halves: 2 x 16 KB)
     if (leader) for (int s = 0; s < kSlots; ++s) mbar_expect_tx_local(BAR(kBarFull + s), 2 * kSlotBytes);
     fence_mbar_init();
@@ -231,22 +231,48 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer (leader CTA only) =================================
+  } else if (warp == 1 || warp == 3) {
+    // ====================== MMA issuers (leader CTA only): warp 1 -> N tile 0, warp 3 -> N tile 1 ===============
+    // Measured with tools/tc_microbench.py (profiles/r01_tc_microbench.txt): one thread that also polls the
+    // full / ready barriers and commits per slot feeds the 64-cycle M128 x N256 MMAs at only ~125-165
+    // cycles each once the epilogue warps compete for its scheduler; two issuing threads (independent
+    // accumulators, so no ordering between them is needed) with their barrier polls issued one step AHEAD
+    // of use keep the tensor pipe at 64 cycles / MMA.
     if (leader && lane == 0) {
-      int slot = 0;
+      const int my_nt = warp == 1 ? 0 : 1;
+      int slot = 0;          // ring position of the next slot use in producer order
       uint32_t ring = 0;
+      auto advance = [&](int n) { slot += n; if (slot >= kSlots) { slot -= kSlots; ring ^= 1u; } };  // n < kSlots
+      // try_wait results obtained ahead of time: {barrier, parity, completed}
+      uint32_t fh_bar = 0, fh_par = 0, fh_ok = 0, ah_bar = 0, ah_par = 0, ah_ok = 0;
+      auto poll = [&](uint32_t bar, uint32_t par) -> uint32_t { return mbar_try_wait(bar, par) ? 1u : 0u; };
+      auto wait_full = [&](int tag) {
+        const uint32_t bar = BAR(kBarFull + slot);
+        if (!(fh_ok && fh_bar == bar && fh_par == ring)) mbar_wait(bar, ring, abort_flag, prm.status, tag + slot);
+        fh_ok = 0;
+        mbar_expect_tx_local(bar, 2 * kSlotBytes);  // arm the slot's next generation
+        tc_fence_after();
+      };
+      auto poll_full_at = [&](int ahead) {   // poll the slot `ahead` uses after the current position
+        int s2 = slot + ahead; uint32_t r2 = ring;
+        if (s2 >= kSlots) { s2 -= kSlots; r2 ^= 1u; }
+        fh_bar = BAR(kBarFull + s2); fh_par = r2; fh_ok = poll(fh_bar, r2);
+      };
       const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
       for (long long it = 0; it < n_iter; ++it) {
         for (int l = 0; l < kNumLayers; ++l) {
           const long long L = it * kNumLayers + l;
           const int buf = (int)(L & 1);
           const uint32_t use = (uint32_t)(L >> 1);
-          TRACE(0, it, l, 0);
+          if (my_nt == 0) TRACE(0, it, l, 0);
           mbar_wait(BAR(kBarAccEmpty + buf), (use & 1u) ^ 1u, abort_flag, prm.status, 200 + buf);
           tc_fence_after();
-          TRACE(0, it, l, 1);
+          if (my_nt == 0) TRACE(0, it, l, 1);
           const int nkb = NetT::nkb(l);
+          const int T = NetT::ntiles(l);
+          const bool small = NetT::small(l, my_nt);
+          const uint32_t idesc = small ? idesc_f16(128, 32) : idesc_f16(128, 256);
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + my_nt * 128);
           // Ordering for accuracy (parity mode, last layer): the tensor core accumulates with truncation, so
           // every MMA added to a LARGE accumulator costs ~1 ulp of it.  The correction products (lo*hi,
           // hi*lo) are 2^-11 of the result: issued first, while the accumulator is still tiny, their
@@ -254,62 +280,72 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           // (96 -> 32 significant truncations).  Other layers keep one sweep (w_hi is streamed once).
           const bool two_sweeps = (passes == 3 && l == kNumLayers - 1);
           for (int sweep = 0; sweep < (two_sweeps ? 2 : 1); ++sweep) {
+            const int planes = (passes == 3 && sweep == 0) ? 2 : 1;   // slot uses per (K block, tile)
             for (int i = 0; i < nkb; ++i) {
+              if (my_nt >= T) { advance(T * planes); continue; }      // single-tile layer: nothing for issuer 1
               const int kbi = NetT::kb_at(l, i);
               const bool is_pe = NetT::is_pe(l, kbi);
               if (sweep == 0) {
                 // layer 0 consumes what the prologue wrote (PE buffer, or the input K blocks of the deformer);
                 // every other layer the K blocks released by the previous layer's epilogue
-                if (l == 0) mbar_wait(BAR(kBarPeReady), (uint32_t)(it & 1), abort_flag, prm.status, 210);
-                else if (!is_pe) mbar_wait(BAR(kBarAReady + kbi), (uint32_t)((l - 1) & 1), abort_flag, prm.status, 220 + kbi);
+                if (l == 0 || !is_pe) {
+                  const uint32_t bar = l == 0 ? BAR(kBarPeReady) : BAR(kBarAReady + kbi);
+                  const uint32_t par = l == 0 ? (uint32_t)(it & 1) : (uint32_t)((l - 1) & 1);
+                  if (!(ah_ok && ah_bar == bar && ah_par == par)) mbar_wait(bar, par, abort_flag, prm.status, 220 + kbi);
+                  ah_ok = 0;
+                }
                 tc_fence_after();
-                if (i == 0) TRACE(0, it, l, 2);
-                if (i == 4) TRACE(0, it, l, 3);
-                if (i == nkb - 1) TRACE(0, it, l, 4);
+                if (my_nt == 0) {
+                  if (i == 0) TRACE(0, it, l, 2);
+                  if (i == 4) TRACE(0, it, l, 3);
+                  if (i == nkb - 1) TRACE(0, it, l, 4);
+                }
               }
               const uint64_t a_hi = smem_desc_sw128(is_pe ? base + kOffPeHi : base + kOffAHi + kbi * 8192);
               const uint64_t a_lo = smem_desc_sw128(is_pe ? base + kOffPeLo : base + kOffALo + kbi * 8192);
-              for (int nt = 0; nt < NetT::ntiles(l); ++nt) {
-                const bool small = NetT::small(l, nt);
-                const uint32_t idesc = small ? idesc_f16(128, 32) : idesc_f16(128, 256);
-                const uint32_t dcol = tmem_base + (uint32_t)(buf * 256 + nt * 128);
-                // ---- slot with w_hi -------------------------------------------------------------------
-                mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 230 + slot);
-                mbar_expect_tx_local(BAR(kBarFull + slot), 2 * kSlotBytes);  // arm the slot's next generation
-                tc_fence_after();
-                uint64_t b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
-                if (!two_sweeps) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                  if (passes == 3) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_lo + 2 * k, b + 2 * k, idesc, 1u);
-                  }
-                } else if (sweep == 0) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_lo + 2 * k, b + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, 1u);
-                }
-                umma_commit_pair(BAR(kBarEmpty + slot), 3);  // cluster CTAs 0 and 1 (the producers)
-                if (++slot == kSlots) { slot = 0; ring ^= 1u; }
-                // ---- slot with w_lo (parity mode; not in the hi*hi sweep) -----------------------------------
-                if (passes == 3 && sweep == 0) {
-                  mbar_wait(BAR(kBarFull + slot), ring, abort_flag, prm.status, 240 + slot);
-                  mbar_expect_tx_local(BAR(kBarFull + slot), 2 * kSlotBytes);
-                  tc_fence_after();
-                  b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, 1u);
-                  umma_commit_pair(BAR(kBarEmpty + slot), 3);
-                  if (++slot == kSlots) { slot = 0; ring ^= 1u; }
-                }
+              advance(my_nt * planes);                                // the lower tile's uses of this K block
+              // ---- slot with w_hi ---------------------------------------------------------------------------
+              wait_full(230);
+              uint64_t b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
+              const int s_hi = slot;
+              advance(1);
+              // poll ahead: this K block's w_lo slot, or the next K block's first slot
+              poll_full_at(planes == 2 ? 0 : (T - 1) * planes);
+              if (sweep == 0 && l > 0 && i + 1 < nkb) {               // ... and the next K block's activations
+                const int kb2 = NetT::kb_at(l, i + 1);
+                if (!NetT::is_pe(l, kb2)) { ah_bar = BAR(kBarAReady + kb2); ah_par = (uint32_t)((l - 1) & 1); ah_ok = poll(ah_bar, ah_par); }
               }
+              if (!two_sweeps) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                if (passes == 3) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_lo + 2 * k, b + 2 * k, idesc, 1u);
+                }
+              } else if (sweep == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_lo + 2 * k, b + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, 1u);
+              }
+              umma_commit_pair(BAR(kBarEmpty + s_hi), 3);  // cluster CTAs 0 and 1 (the producers)
+              // ---- slot with w_lo (parity mode; not in the hi*hi sweep) --------------------------------------
+              if (planes == 2) {
+                wait_full(240);
+                b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
+                const int s_lo = slot;
+                advance(1);
+                poll_full_at((T - 1) * planes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_pair(dcol, a_hi + 2 * k, b + 2 * k, idesc, 1u);
+                umma_commit_pair(BAR(kBarEmpty + s_lo), 3);
+              }
+              advance((T - 1 - my_nt) * planes);                      // the upper tile's uses of this K block
             }
           }
-          umma_commit_pair(BAR(kBarAccFull + buf), pair_mask);
-          TRACE(0, it, l, 5);
+          umma_commit_pair(BAR(kBarAccFull + buf), pair_mask);   // one arrival per issuer
+          if (my_nt == 0) TRACE(0, it, l, 5);
           if (l == NetT::kInFreeLayer) umma_commit_pair(BAR(kBarPeFree), pair_mask);  // prologue may refill its block
         }
       }
