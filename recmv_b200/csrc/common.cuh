@@ -209,10 +209,13 @@ __host__ __device__ constexpr int panel_base(int l) {
   return l == 0 ? 0 : (l <= 4 ? 1 + 8 * (l - 1) : 34 + 8 * (l - 5));
 }
 __host__ __device__ constexpr int num_panels(int l) { return l == 0 ? 1 : (l == 4 ? 9 : 8); }
+// softplus(beta=100) evaluated in base 2: u = 100 log2(e) z;  softplus = ln2/100 * log2(1 + 2^u)
+constexpr float kSoftplusLog2Scale = 144.26950408889634f;   // 100 * log2(e)
 struct PackedLayout {
   size_t w32_off[kNumLayers];   // fp32 [K, Npad32] (transposed) for the SIMT kernel
   size_t b32_off[kNumLayers];   // fp32 [512] bias padded with zeros
-  size_t bias_all_off;          // == b32_off[0]; the 9 padded biases are contiguous, stride 512 floats
+  size_t bias_all_off;          // == b32_off[0]; the 9 padded biases are contiguous, stride 512 floats;
+                                // a second [9][512] plane holds b * kSoftplusLog2Scale
   size_t f16_off;               // fp16 panels: [2 planes][66 panels][512][64]
   size_t total;
 };

@@ -22,7 +22,7 @@ PackedLayout packed_layout() {
   PackedLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) & ~(size_t)1023; return o; };
-  L.bias_all_off = take((size_t)kNumLayers * 512 * 4);
+  L.bias_all_off = take((size_t)2 * kNumLayers * 512 * 4);   // plane 0: b; plane 1: b * 100 log2(e) (tcgen05 epilogue)
   for (int l = 0; l < kNumLayers; ++l) L.b32_off[l] = L.bias_all_off + (size_t)l * 512 * 4;
   for (int l = 0; l < kNumLayers; ++l) L.w32_off[l] = take((size_t)kKfull(l) * kNpad32(l) * 4);
   L.f16_off = take((size_t)2 * kNumPanels * 512 * 64 * 2);
@@ -60,8 +60,10 @@ __global__ void __launch_bounds__(256) pack_layer_kernel(const float* __restrict
     int k = (int)(i / npad32), n = (int)(i - (int64_t)k * npad32);
     w32t[i] = n < out ? W[(size_t)n * in + k] * scale : 0.f;
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 512; i += gridDim.x * blockDim.x)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 512; i += gridDim.x * blockDim.x) {
     bpad[i] = i < out ? b[i] : 0.f;
+    bpad[kNumLayers * 512 + i] = i < out ? b[i] * kSoftplusLog2Scale : 0.f;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

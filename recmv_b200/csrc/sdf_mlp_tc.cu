@@ -29,8 +29,14 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreads = 448;  // 4 role warps + 8 epilogue warps + 2 prologue warps
-constexpr int kEpiWarps = 8;
+#ifndef RECMV_EPI_WARPS
+#define RECMV_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = RECMV_EPI_WARPS;         // 8 or 16: 2 or 4 warps per TMEM lane quadrant
+constexpr int kEpiGroups = kEpiWarps / 4;          // warps sharing a quadrant split every 64-column K block ...
+constexpr int kCw = 64 / kEpiGroups;               // ... into chunks of kCw columns
+constexpr int kThreads = 32 * (4 + kEpiWarps + 2); // 4 role warps + epilogue warps + 2 prologue warps
+static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps");
 constexpr int kPairs = 1;  // MMA pairs per cluster sharing every weight tile through TMA multicast.
                            // 2 was measured (profiles/r01_notes.md): correct, halves L2->SM weight traffic, but no
                            // faster (the MMA phase is bound by the pair's operand path, not by L2) and clusters of 4
@@ -104,13 +110,21 @@ __device__ __forceinline__ int kb_order(int l, int i) {
   return (i & 4) | ((i & 1) << 1) | ((i >> 1) & 1);  // 0,2,1,3,4,6,5,7
 }
 
-// softplus(beta=100, threshold=20) on the MUFU pipe: ex2.approx / lg2.approx (2^-21-grade), 8-way ILP at
-// the call site.  (Accurate expf/log1pf cost ~60 dependent instructions per activation.)
-__device__ __forceinline__ float softplus100_fast(float z) {
-  const float t = 100.f * z;
-  const float e = __expf(fminf(t, 20.f));
-  const float y = __logf(1.f + e) * 0.01f;
-  return t > 20.f ? z : y;
+// softplus(beta=100, threshold=20) * kActScale straight from the raw accumulator, in base 2:
+//   u = acc * (2^-16 * 100 log2 e) + b * 100 log2 e  (the bias plane is pre-multiplied at pack time)
+//   u <= 20 log2 e : ln2/100 * log2(1 + 2^u)     else : z = u / (100 log2 e)        (torch's threshold branch)
+// 9 instructions per activation (FFMA FMNMX EX2 FADD LG2 FMUL FMUL FSETP FSEL); ex2/lg2 .ftz skip the denormal
+// range fix-ups of __expf/__logf (3 more FMUL + 2 predicates each).
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float softplus100_scaled(uint32_t acc_bits, float bias_u) {
+  constexpr float kU1 = kAccUnscale * kSoftplusLog2Scale;
+  constexpr float kUThr = 20.f * 1.4426950408889634f;
+  constexpr float kC1 = 0.0069314718055994531f * kActScale;    // ln2 / 100
+  constexpr float kC2 = kActScale / kSoftplusLog2Scale;
+  const float u = fmaf(__uint_as_float(acc_bits), kU1, bias_u);
+  const float y = lg2_ftz(1.f + ex2_ftz(fminf(u, kUThr))) * kC1;
+  return u > kUThr ? u * kC2 : y;
 }
 
 // value row: softplus100(z); tangent row: z_tangent * sigmoid(100 z_value)  (d softplus / dz; torch's
@@ -182,7 +196,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   if (threadIdx.x == 0) {
     *abort_flag = 0;
     for (int s = 0; s < kSlots; ++s) { mbar_init(BAR(kBarFull + s), 1); mbar_init(BAR(kBarEmpty + s), kPairs); }
-    for (int k = 0; k < 8; ++k) mbar_init(BAR(kBarAReady + k), 8);
+    for (int k = 0; k < 8; ++k) mbar_init(BAR(kBarAReady + k), 4 * kEpiGroups);
     mbar_init(BAR(kBarPeReady), 4);
     mbar_init(BAR(kBarPeFree), 2);                               // one commit per MMA issuer
     for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 2); mbar_init(BAR(kBarAccEmpty + b), 2 * kEpiWarps); }
@@ -246,9 +260,18 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
       // try_wait results obtained ahead of time: {barrier, parity, completed}
       uint32_t fh_bar = 0, fh_par = 0, fh_ok = 0, ah_bar = 0, ah_par = 0, ah_ok = 0;
       auto poll = [&](uint32_t bar, uint32_t par) -> uint32_t { return mbar_try_wait(bar, par) ? 1u : 0u; };
+#ifdef RECMV_TC_WAITSTATS
+      long long ws_full = 0, ws_nblock = 0, ws_a = 0;
+#endif
       auto wait_full = [&](int tag) {
         const uint32_t bar = BAR(kBarFull + slot);
+#ifdef RECMV_TC_WAITSTATS
+        const long long w0 = clock64();
+        if (!(fh_ok && fh_bar == bar && fh_par == ring)) { mbar_wait(bar, ring, abort_flag, prm.status, tag + slot); ++ws_nblock; }
+        ws_full += clock64() - w0;
+#else
         if (!(fh_ok && fh_bar == bar && fh_par == ring)) mbar_wait(bar, ring, abort_flag, prm.status, tag + slot);
+#endif
         fh_ok = 0;
         mbar_expect_tx_local(bar, 2 * kSlotBytes);  // arm the slot's next generation
         tc_fence_after();
@@ -291,8 +314,14 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                 if (l == 0 || !is_pe) {
                   const uint32_t bar = l == 0 ? BAR(kBarPeReady) : BAR(kBarAReady + kbi);
                   const uint32_t par = l == 0 ? (uint32_t)(it & 1) : (uint32_t)((l - 1) & 1);
+#ifdef RECMV_TC_WAITSTATS
+                  const long long w0 = clock64();
+#endif
                   if (!(ah_ok && ah_bar == bar && ah_par == par)) mbar_wait(bar, par, abort_flag, prm.status, 220 + kbi);
                   ah_ok = 0;
+#ifdef RECMV_TC_WAITSTATS
+                  ws_a += clock64() - w0;
+#endif
                 }
                 tc_fence_after();
                 if (my_nt == 0) {
@@ -346,6 +375,13 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           }
           umma_commit_pair(BAR(kBarAccFull + buf), pair_mask);   // one arrival per issuer
           if (my_nt == 0) TRACE(0, it, l, 5);
+#ifdef RECMV_TC_WAITSTATS
+          if (prm.trace && blockIdx.x == 0 && it < 2) {   // per layer: cycles in weight-slot waits, blocking waits, K-block waits
+            unsigned long long* t = prm.trace + (((0 * 2 + it) * 9 + l) << 4) + 6 + 3 * my_nt;
+            t[0] = (unsigned long long)ws_full; t[1] = (unsigned long long)ws_nblock; t[2] = (unsigned long long)ws_a;
+          }
+          ws_full = ws_nblock = ws_a = 0;
+#endif
           if (l == NetT::kInFreeLayer) umma_commit_pair(BAR(kBarPeFree), pair_mask);  // prologue may refill its block
         }
       }
@@ -353,7 +389,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ================================ epilogue (both CTAs) =========================================
     const int q = warp & 3;               // TMEM lane quadrant == warp index % 4
-    const int grp = (warp - 4) >> 2;      // which 32-column half of every K block of this quadrant
+    const int grp = (warp - 4) >> 2;      // which kCw-column part of every K block of this quadrant
     const int row = (q & 1) * 32 + lane;  // tile row owned by this thread (lanes 64.. mirror rows 0..63)
     const int half = q >> 1;              // which 128-column half of each 256-wide N tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -367,35 +403,56 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         const long long L = it * kNumLayers + l;
         const int buf = (int)(L & 1);
         const uint32_t use = (uint32_t)(L >> 1);
-        if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 0);
+        const float* bias = prm.bias + l * 512;
+        const bool hidden = l < kNumLayers - 1;
+        // hidden layers: 4 chunks of kCw columns per warp, chunk c = (N tile c >> 1, K block c & 1 of this half)
+        const float* bsel = (!kJvp && kNet == 0) ? bias + kNumLayers * 512 : bias;   // SDF: the b * 100 log2 e plane
+        auto f0_of = [&](int c) { return (c >> 1) * 256 + half * 128 + (c & 1) * 64 + grp * kCw; };
+        float bcur[kCw];
+        if (hidden) {   // the first chunk's biases travel while this warp waits for the accumulator
+#pragma unroll
+          for (int j = 0; j < kCw / 4; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(bsel + f0_of(0) + 4 * j));
+            bcur[4 * j] = t.x; bcur[4 * j + 1] = t.y; bcur[4 * j + 2] = t.z; bcur[4 * j + 3] = t.w;
+          }
+        }
+        const bool tr = lane == 0 && (warp == 4 || warp == 3 + kEpiWarps);
+        const int trole = warp == 4 ? 1 : 2;
+        if (tr) TRACE(trole, it, l, 0);
         mbar_wait(BAR(kBarAccFull + buf), use & 1u, abort_flag, prm.status, 300 + q);
         tc_fence_after();
-        if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 1);
-        const float* bias = prm.bias + l * 512;
-        for (int nt = 0; nt < NetT::ntiles(l); ++nt) {
-          const bool small = NetT::small(l, nt);
-          if (small && grp != 0) continue;  // the 32-wide tail tile has a single 16-column group per half
-          for (int cc = 0; cc < (small ? 32 : 64); cc += 32) {
-            const int c0 = small ? cc : cc * 2 + grp * 32;  // K block (cc/32) of this half, 32-column part grp
-            uint32_t r[32];
-            tmem_ld32(tmem_base + lane_addr + (uint32_t)(buf * 256 + nt * 128 + c0), r);
+        if (tr) TRACE(trole, it, l, 1);
+        if (hidden) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int f0 = f0_of(c);
+            uint32_t r[kCw];
+            tmem_ld_cols<kCw>(tmem_base + lane_addr + (uint32_t)(buf * 256 + (c >> 1) * 128 + (c & 1) * 64 + grp * kCw), r);
+            float bnext[kCw];
+            if (c < 3) {   // next chunk's biases: in flight during this chunk's arithmetic
+#pragma unroll
+              for (int j = 0; j < kCw / 4; ++j) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(bsel + f0_of(c + 1) + 4 * j));
+                bnext[4 * j] = t.x; bnext[4 * j + 1] = t.y; bnext[4 * j + 2] = t.z; bnext[4 * j + 3] = t.w;
+              }
+            }
             tmem_ld_wait();
-            const int f0 = small ? nt * 256 + half * 16 + c0 : nt * 256 + half * 128 + c0;
-            if (prm.dbg_out && prm.dbg_layer == l && tile == 0 && !small) {  // cluster 0, pair 0
+            if (c == 0 && tr) TRACE(trole, it, l, 5);
+            if (prm.dbg_out && prm.dbg_layer == l && tile == 0) {  // cluster 0, pair 0
               float* d = prm.dbg_out + ((size_t)rank * kRowsPerCta + row) * 512 + f0;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) d[c] = __uint_as_float(r[c]) * kAccUnscale;
+              for (int cc = 0; cc < kCw; ++cc) d[cc] = __uint_as_float(r[cc]) * kAccUnscale;
             }
-            if (l < kNumLayers - 1) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int f = f0 + 8 * j;
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + f));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + f + 4));
-                float v[8] = {fmaf(__uint_as_float(r[8 * j + 0]), kAccUnscale, b0.x), fmaf(__uint_as_float(r[8 * j + 1]), kAccUnscale, b0.y),
-                              fmaf(__uint_as_float(r[8 * j + 2]), kAccUnscale, b0.z), fmaf(__uint_as_float(r[8 * j + 3]), kAccUnscale, b0.w),
-                              fmaf(__uint_as_float(r[8 * j + 4]), kAccUnscale, b1.x), fmaf(__uint_as_float(r[8 * j + 5]), kAccUnscale, b1.y),
-                              fmaf(__uint_as_float(r[8 * j + 6]), kAccUnscale, b1.z), fmaf(__uint_as_float(r[8 * j + 7]), kAccUnscale, b1.w)};
+            for (int j = 0; j < kCw / 8; ++j) {
+              const int f = f0 + 8 * j;
+              float v[8];
+              if (!kJvp && kNet == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = softplus100_scaled(r[8 * j + e], bcur[8 * j + e]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[8 * j + e]), kAccUnscale, bcur[8 * j + e]);
                 if (kJvp) {
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
@@ -403,27 +460,45 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                     const float z_val = __shfl_sync(0xffffffffu, z_own, lane & ~3);  // the point's value row
                     v[e] = act_jvp(z_own, z_val, is_value) * kActScale;
                   }
-                } else if (kNet == 0) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = softplus100_fast(v[e]) * kActScale;
                 } else {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f) * kActScale;   // ReLU
+                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f) * kActScale;   // ReLU (deformer)
                 }
-                uint4 hi, lo;
-                split8(v, hi, lo);
-                const int kb = f >> 6, chunk = (f & 63) >> 3;
-                const uint32_t off = (uint32_t)kb * 8192u + sw128_offset(row, chunk);
-                st_shared_v4(base + kOffAHi + off, hi);
-                st_shared_v4(base + kOffALo + off, lo);
               }
-              {  // this warp's 32 columns of K block (f0 >> 6) of the next layer's input are complete
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(BAR(kBarAReady + (f0 >> 6)), lrank);
-                if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 2 + nt);
-              }
-            } else if (kNet == 1) {
+              uint4 hi, lo;
+              split8(v, hi, lo);
+              const int kb = f >> 6, chunk = (f & 63) >> 3;
+              const uint32_t off = (uint32_t)kb * 8192u + sw128_offset(row, chunk);
+              st_shared_v4(base + kOffAHi + off, hi);
+              st_shared_v4(base + kOffALo + off, lo);
+            }
+            if (c == 0 && tr) TRACE(trole, it, l, 6);
+            // this warp's kCw columns of K block (f0 >> 6) of the next layer's input are complete
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(BAR(kBarAReady + (f0 >> 6)), lrank);
+            if (tr) TRACE(trole, it, l, c == 0 ? 7 : 2 + (c >> 1));
+            if (c < 3) {
+#pragma unroll
+              for (int e = 0; e < kCw; ++e) bcur[e] = bnext[e];
+            }
+          }
+        }
+        for (int nt = 0; !hidden && nt < NetT::ntiles(l); ++nt) {
+          const bool small = NetT::small(l, nt);
+          if (small && grp != 0) continue;  // the 32-wide tail tile has a single 16-column group per half
+          for (int kbl = 0; kbl < (small ? 1 : 2); ++kbl) {
+            const int c0 = small ? 0 : kbl * 64 + grp * kCw;  // K block kbl of this 128-column half, part grp
+            uint32_t r[kCw];
+            tmem_ld_cols<kCw>(tmem_base + lane_addr + (uint32_t)(buf * 256 + nt * 128 + c0), r);
+            tmem_ld_wait();
+            const int f0 = small ? nt * 256 + half * 16 + c0 : nt * 256 + half * 128 + c0;
+            if (prm.dbg_out && prm.dbg_layer == l && tile == 0 && !small) {  // cluster 0, pair 0
+              float* d = prm.dbg_out + ((size_t)rank * kRowsPerCta + row) * 512 + f0;
+#pragma unroll
+              for (int c = 0; c < kCw; ++c) d[c] = __uint_as_float(r[c]) * kAccUnscale;
+            }
+            if (kNet == 1) {
               // deformer: columns 0..2 of the tail tile = offset; out = p + offset, then LBS forward
               if (p < prm.P && half == 0 && c0 == 0) {
                 const float dx = fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias + 0));
@@ -454,7 +529,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                 if (f0 == 0) prm.out_sdf[p] = ok ? fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias)) : kInvalidSdf;
                 if (prm.out_feat) {
 #pragma unroll
-                  for (int c = 0; c < 32; ++c) {
+                  for (int c = 0; c < kCw; ++c) {
                     const int f = f0 + c;
                     if (f > 0) prm.out_feat[p * 256 + (f - 1)] = fmaf(__uint_as_float(r[c]), kAccUnscale, __ldg(bias + f));
                   }
@@ -468,7 +543,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(BAR(kBarAccEmpty + buf), lrank);
-        if (lane == 0 && (warp == 4 || warp == 11)) TRACE(warp == 4 ? 1 : 2, it, l, 4);
+        if (tr) TRACE(trole, it, l, 4);
       }
     }
   } else if (warp >= 4 + kEpiWarps) {

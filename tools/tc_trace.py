@@ -28,8 +28,11 @@ for passes in (3, 1):
     for it in range(2):
         for l in range(9):
             m = [int(v) - t0 if v else -1 for v in t[0, it, l, :6]]
-            e1 = [int(v) - t0 if v else -1 for v in t[1, it, l, :5]]
+            e1 = [int(v) - t0 if v else -1 for v in t[1, it, l, :8]]
             e2 = [int(v) - t0 if v else -1 for v in t[2, it, l, :5]]
             pr = [int(v) - t0 if v else -1 for v in t[3, it, l, :2]]
-            print(f"it{it} L{l} MMA[start,accfree,kb0rdy,kb4rdy,lastkb,commit]={m}  EPIw4[wait,go,nt0,nt1,done]={e1}  "
+            ws = [int(v) for v in t[0, it, l, 6:12]]
+            if any(ws):
+                print(f"      issuer0: slot-wait cycles={ws[0]} blocking={ws[1]} kblock-wait={ws[2]} | issuer1: {ws[3]} {ws[4]} {ws[5]}")
+            print(f"it{it} L{l} MMA[start,accfree,kb0rdy,kb4rdy,lastkb,commit]={m}  EPIw4[wait,go,nt0,nt1,done,c0:ld,c0:stored,c0:arrived]={e1}  "
                   f"EPIw11={e2} PROD[start,lastkb]={pr}")
