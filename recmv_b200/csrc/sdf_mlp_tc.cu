@@ -38,9 +38,10 @@ constexpr int kCw = 64 / kEpiGroups;               // ... into chunks of kCw col
 constexpr int kThreads = 32 * (4 + kEpiWarps + 2); // 4 role warps + epilogue warps + 2 prologue warps
 static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps");
 constexpr int kPairs = 1;  // MMA pairs per cluster sharing every weight tile through TMA multicast.
-                           // 2 was measured (profiles/r01_notes.md): correct, halves L2->SM weight traffic, but no
-                           // faster (the MMA phase is bound by the pair's operand path, not by L2) and clusters of 4
-                           // only fit on 132 of the 148 SMs.
+                           // 2 was measured twice (profiles/r01_notes.md): correct and it halves the L2 reads (SM clock
+                           // under the power cap rises 1.73 -> 1.85 GHz), but the pairs then consume the weight
+                           // stream in lockstep and the frame gets SLOWER (tc3 1.41 -> 1.32 M rays/s, tc1 2.36 -> 2.08);
+                           // clusters of 4 also only fit on 132 of the 148 SMs.
 constexpr int kRowsPerCta = 64;
 constexpr int kSlots = 5;
 constexpr uint32_t kSlotBytes = 16384;
