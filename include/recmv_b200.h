@@ -162,6 +162,18 @@ RECMV_API int recmv_deformer_fwd(const float* ps, const float* conds, const int6
                        const recmv_voxel_t* vox /*host, may be NULL*/, float* out_translated,
                        float* out_offset, float* out_posed, int64_t P, int mode, recmv_stream_t stream);
 
+/* ---- A8: RenderingNetwork_view_norm.forward, mode 'idr' (model/RenderNet.py:59-96) in one launch -----------------
+ * cat[points 3 | PE4(view_dirs) 27 | normals 3 | feature_vectors 256] = 289 -> 512 x4 ReLU -> 3 -> tanh.
+ * pack: effective (weight-norm materialised) W_l [out,in] row-major fp32 concatenated, l = 0..4; b likewise.
+ * pe_w [8] host = annealing weights of the 4-band view-direction encoding.  All tensors [P,*] row-major fp32.
+ * TC modes only.                                                                                              */
+RECMV_API size_t recmv_rendernet_packed_bytes(void);
+RECMV_API int recmv_rendernet_pack_weights(const float* W_all, const float* b_all, void* packed,
+                                 recmv_stream_t stream);
+RECMV_API int recmv_rendernet_fwd(const float* points, const float* normals, const float* view_dirs,
+                        const float* feats, const void* packed, const float* pe_w /*host*/, float* out_rgb,
+                        int64_t P, int mode, recmv_stream_t stream);
+
 /* Non-blocking health check of the tcgen05 path on the current device: every mbarrier wait in the kernel is
  * bounded; a wait that times out records {code, barrier tag, block} in mapped host memory and later launches
  * are refused with RECMV_E_DEVICE.  info may be NULL; clear != 0 resets the record.                        */

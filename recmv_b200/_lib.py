@@ -67,6 +67,10 @@ SIGNATURES = {
     "recmv_deformer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, POINTER(c_float),
                                    c_void_p, c_void_p, POINTER(Voxel), c_void_p, c_void_p, c_void_p, c_int64,
                                    c_int, c_void_p]),
+    "recmv_rendernet_packed_bytes": (c_size_t, []),
+    "recmv_rendernet_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "recmv_rendernet_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p, c_int64,
+                                    c_int, c_void_p]),
     "recmv_tc_microbench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "recmv_check_async_errors": (c_int, [POINTER(c_int), c_int]),
     "recmv_sdf_mlp_tc_debug": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int64,

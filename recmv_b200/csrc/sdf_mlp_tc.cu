@@ -92,6 +92,11 @@ struct TcParams {
   float* out_translated;         // [P,3]  p + delta
   float* out_offset;             // [P,3]  delta (MLPTranslator.offset), optional
   float* out_posed;              // [P,3]  LBS(p + delta), optional
+  // colour network (kNet == 2): cat[p, PE4(view), n, feat] = 289 -> 512 x4 (ReLU) -> 3 -> tanh; src.x = points
+  const float* normals;          // [P,3]
+  const float* view_dirs;        // [P,3]
+  const float* feats;            // [P,256]
+  float* out_rgb;                // [P,3]
 };
 #define TRACE(role, it, l, ev)                                                                     \
   do {                                                                                             \
@@ -158,6 +163,18 @@ template <> struct Net<1> {
   __device__ static int pbase(int l) { return l == 0 ? 0 : 3 + 8 * (l - 1); }
   __device__ static int kb_at(int l, int i) { return l == 0 ? i : ((i & 4) | ((i & 1) << 1) | ((i >> 1) & 1)); }
   __device__ static bool is_pe(int, int) { return false; }   // the input block lives in the activation buffer
+  __device__ static int ntiles(int l) { return l == 4 ? 1 : 2; }
+  __device__ static bool small(int l, int) { return l == 4; }
+};
+
+// RenderingNetwork_view_norm, mode 'idr' (model/RenderNet.py:59-96): [p 3 | PE4(v) 27 | n 3 | feat 256 | 0 x31] = 5 K
+// blocks -> 512 x4 (ReLU) -> 3 -> tanh
+template <> struct Net<2> {
+  static constexpr int kLayers = 5, kPanels = 37, kInFreeLayer = 4;
+  __device__ static int nkb(int l) { return l == 0 ? 5 : 8; }
+  __device__ static int pbase(int l) { return l == 0 ? 0 : 5 + 8 * (l - 1); }
+  __device__ static int kb_at(int l, int i) { return l == 0 ? i : ((i & 4) | ((i & 1) << 1) | ((i >> 1) & 1)); }
+  __device__ static bool is_pe(int, int) { return false; }
   __device__ static int ntiles(int l) { return l == 4 ? 1 : 2; }
   __device__ static bool small(int l, int) { return l == 4; }
 };
@@ -499,7 +516,14 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
 #pragma unroll
               for (int c = 0; c < kCw; ++c) d[c] = __uint_as_float(r[c]) * kAccUnscale;
             }
-            if (kNet == 1) {
+            if (kNet == 2) {
+              // colour network: columns 0..2 of the tail tile -> tanh
+              if (p < prm.P && half == 0 && c0 == 0) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                  prm.out_rgb[3 * p + c] = tanhf(fmaf(__uint_as_float(r[c]), kAccUnscale, __ldg(bias + c)));
+              }
+            } else if (kNet == 1) {
               // deformer: columns 0..2 of the tail tile = offset; out = p + offset, then LBS forward
               if (p < prm.P && half == 0 && c0 == 0) {
                 const float dx = fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias + 0));
@@ -555,7 +579,50 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
       const long long p = kJvp ? tile * 32 + (long long)rank * 16 + (row >> 2)
                                : tile * 128 + (long long)rank * kRowsPerCta + row;
       bool ok = true;
-      if (kNet == 1) {
+      if (kNet == 2) {
+        // colour-network input row, 8 columns at a time straight into the activation buffer (K blocks 0..4)
+        float head[40];   // [p 3 | PE4(v) 27 | n 3 | feat 0..6]
+#pragma unroll
+        for (int e = 0; e < 40; ++e) head[e] = 0.f;
+        const bool live = p < prm.P;
+        const float* ft = prm.feats + (size_t)(live ? p : 0) * 256;
+        if (live) {
+          float pe[39];
+          positional_encode(__ldg(prm.view_dirs + 3 * p), __ldg(prm.view_dirs + 3 * p + 1), __ldg(prm.view_dirs + 3 * p + 2),
+                            prm.pw.w, pe);   // the first 27 entries of a 6-band encoding are the 4-band encoding
+#pragma unroll
+          for (int e = 0; e < 3; ++e) { head[e] = __ldg(prm.src.x + 3 * p + e); head[30 + e] = __ldg(prm.normals + 3 * p + e); }
+#pragma unroll
+          for (int e = 0; e < 27; ++e) head[3 + e] = pe[e];
+#pragma unroll
+          for (int e = 0; e < 7; ++e) head[33 + e] = __ldg(ft + e);
+        }
+        if (it > 0) mbar_wait(BAR(kBarPeFree), (uint32_t)((it - 1) & 1), abort_flag, prm.status, 400);
+#pragma unroll 1
+        for (int chunk = 0; chunk < 40; ++chunk) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col = 8 * chunk + e;              // feature j sits in column 33 + j
+            v[e] = (live && col >= 40 && col < 289) ? __ldg(ft + (col - 33)) : 0.f;
+          }
+          if (chunk < 5) {
+#pragma unroll
+            for (int c5 = 0; c5 < 5; ++c5)
+              if (chunk == c5) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = head[8 * c5 + e];
+              }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= kActScale;
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          const uint32_t off = (uint32_t)(chunk >> 3) * 8192u + sw128_offset(row, chunk & 7);
+          st_shared_v4(base + kOffAHi + off, hi);
+          st_shared_v4(base + kOffALo + off, lo);
+        }
+      } else if (kNet == 1) {
         // deformer input row: [PE(p) (39) | cond[frame] (128) | 0 (25)] = three 64-wide K blocks written into the
         // activation buffer itself (free again once the previous tile's last layer has been issued and done)
         float in[192];
@@ -669,6 +736,7 @@ int tc_prepare_launch(int dev) {
   cudaError_t e = cudaFuncSetAttribute(sdf_tc_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return (int)e;
   done[dev & 15] = true;
   return 0;
@@ -719,7 +787,7 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   int s0 = tc_status_record(dev, &sd);
   if (s0) return s0;
   if (sd->code != 0) return RECMV_E_DEVICE;  // a previous launch on this device aborted
-  TcParams prm;
+  TcParams prm = {};
   prm.src = src; prm.pw = pw;
   prm.bias = (const float*)(pb + L.bias_all_off);
   prm.out_sdf = out_sdf; prm.out_feat = out_feat; prm.P = P; prm.passes = passes; prm.status = sd;
@@ -861,6 +929,86 @@ extern "C" int recmv_deformer_fwd(const float* ps, const float* conds, const int
   int maxc = tc_max_clusters(dev);
   int clusters = (int)(want < maxc ? want : maxc);
   sdf_tc_kernel<false, 1><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
+  return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Colour network: RenderingNetwork_view_norm, mode 'idr' (model/RenderNet.py:59-96)
+// ---------------------------------------------------------------------------------------------------------
+namespace recmv {
+namespace {
+constexpr int kRgbLayers = 5, kRgbPanels = 37;
+constexpr int rgb_in(int l) { return l == 0 ? 289 : 512; }
+constexpr int rgb_out(int l) { return l == 4 ? 3 : 512; }
+constexpr int rgb_pbase(int l) { return l == 0 ? 0 : 5 + 8 * (l - 1); }
+constexpr int rgb_npanels(int l) { return l == 0 ? 5 : 8; }
+DeformLayout rgb_layout() {
+  DeformLayout L;
+  L.bias_off = 0;
+  L.f16_off = ((size_t)kRgbLayers * 512 * 4 + 1023) & ~(size_t)1023;
+  L.total = L.f16_off + (size_t)2 * kRgbPanels * 512 * 64 * 2;
+  return L;
+}
+TmapCacheEntry g_rgb_tmap[16];
+}  // namespace
+}  // namespace recmv
+
+extern "C" size_t recmv_rendernet_packed_bytes(void) { return rgb_layout().total; }
+
+extern "C" int recmv_rendernet_pack_weights(const float* W_all, const float* b_all, void* packed,
+                                            recmv_stream_t stream) {
+  if (!W_all || !b_all || !packed) return RECMV_E_NULL;
+  if (((uintptr_t)packed & 1023) != 0) return RECMV_E_SHAPE;
+  DeformLayout L = rgb_layout();
+  char* base = (char*)packed;
+  size_t woff = 0, boff = 0;
+  for (int l = 0; l < kRgbLayers; ++l) {
+    pack_plain_layer_kernel<<<stride_grid((int64_t)rgb_npanels(l) * 512 * 64, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+        W_all + woff, b_all + boff, rgb_out(l), rgb_in(l), rgb_pbase(l), rgb_npanels(l),
+        (float*)(base + L.bias_off) + l * 512, (__half*)(base + L.f16_off), kRgbPanels);
+    int s = launch_status();
+    if (s) return s;
+    woff += (size_t)rgb_in(l) * rgb_out(l);
+    boff += rgb_out(l);
+  }
+  return RECMV_OK;
+}
+
+extern "C" int recmv_rendernet_fwd(const float* points, const float* normals, const float* view_dirs,
+                                   const float* feats, const void* packed, const float* pe_w, float* out_rgb,
+                                   int64_t P, int mode, recmv_stream_t stream) {
+  if (P < 0) return RECMV_E_SHAPE;
+  if (P == 0) return RECMV_OK;
+  if (!points || !normals || !view_dirs || !feats || !packed || !pe_w || !out_rgb) return RECMV_E_NULL;
+  if (mode != RECMV_MLP_TC_F16X3 && mode != RECMV_MLP_TC_F16X1) return RECMV_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DeformLayout L = rgb_layout();
+  const char* pb = (const char*)packed;
+  TmapCacheEntry& tc_ = g_rgb_tmap[dev & 15];
+  if (tc_.base != pb + L.f16_off) {
+    int s = make_panel_tmap(&tc_.m128, pb + L.f16_off, (uint64_t)2 * kRgbPanels * 512, 128);
+    if (s) return s;
+    tc_.base = pb + L.f16_off;
+  }
+  int s0 = tc_prepare_launch(dev);
+  if (s0) return s0;
+  DevStatus* sd = nullptr;
+  s0 = tc_status_record(dev, &sd);
+  if (s0) return s0;
+  if (sd->code != 0) return RECMV_E_DEVICE;
+  TcParams prm = {};
+  prm.src.x = points; prm.src.S = 1;
+  for (int i = 0; i < 12; ++i) prm.pw.w[i] = i < 8 ? pe_w[i] : 0.f;
+  prm.bias = (const float*)(pb + L.bias_off);
+  prm.P = P; prm.passes = mode == RECMV_MLP_TC_F16X3 ? 3 : 1; prm.status = sd; prm.dbg_layer = -1;
+  prm.normals = normals; prm.view_dirs = view_dirs; prm.feats = feats; prm.out_rgb = out_rgb;
+  int64_t tiles = (P + 127) / 128;
+  int64_t want = (tiles + kPairs - 1) / kPairs;
+  int maxc = tc_max_clusters(dev);
+  int clusters = (int)(want < maxc ? want : maxc);
+  sdf_tc_kernel<false, 2><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
   return launch_status();
 }
 

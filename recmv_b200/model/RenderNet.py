@@ -1,9 +1,12 @@
 """IDR colour MLP with the reference's API (model/RenderNet.py:10-103): cat[p, PE4(v), n, feat] = 289
--> 512 x4 ReLU -> 3 -> tanh, weight-normed.  Evaluated once per RAY (not per sample); runs as a torch
-graph over cuBLAS in this round (SURVEY 8a row A8, 1.9 MFLOP/ray = 0.7 % of the per-ray work)."""
+-> 512 x4 ReLU -> 3 -> tanh, weight-normed.  Evaluated once per RAY (not per sample).  Without an autograd
+graph (and for the standard 'idr' 289-wide configuration) the whole network is ONE launch of the tcgen05 engine
+(recmv_rendernet_fwd: input row assembled in shared memory, 5 layers on tensor cores, tanh in the epilogue);
+with a graph it runs as torch ops over cuBLAS (SURVEY 8a row A8, 1.9 MFLOP/ray = 0.7 % of the per-ray work)."""
 import torch
 import torch.nn as nn
 
+from .. import ops
 from .Embedder import get_embedder, ratio_to_weights
 
 
@@ -31,9 +34,40 @@ class RenderingNetwork_view_norm(nn.Module):
             setattr(self, "lin" + str(l), lin)
         self.relu = nn.ReLU()
         self.tanh = nn.Tanh()
+        self.mlp_mode = None
+        self.last_path = None
+        self._packed, self._packed_key = None, None
+        self.fusable = (mode == 'idr' and multires_v == 4 and multires_n == 0 and feature_vector_size == 256
+                        and d_in == 9 and d_out == 3 and list(dims[1:-1]) == [512] * 4)
+
+    def packed_weights(self):
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or key != self._packed_key:
+            with torch.no_grad():
+                Ws, bs = [], []
+                for l in range(self.num_layers - 1):
+                    lin = getattr(self, "lin" + str(l))
+                    if hasattr(lin, "weight_g"):
+                        v, g = lin.weight_v, lin.weight_g
+                        Ws.append(v * (g / v.norm(dim=1, keepdim=True)))
+                    else:
+                        Ws.append(lin.weight)
+                    bs.append(lin.bias)
+                self._packed = ops.rendernet_pack_weights(Ws, bs)
+            self._packed_key = key
+        return self._packed
 
     def forward(self, points, normals, view_dirs, feature_vectors, ratio):
         ratio = ratio['renderRatio']
+        tensors = [points, normals, view_dirs, feature_vectors] + list(self.parameters())
+        needs_graph = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+        if (self.fusable and points.is_cuda and points.dim() == 2 and not needs_graph
+                and self.mlp_mode != ops.MLP_FP32_SIMT):
+            self.last_path = "fused"
+            return ops.rendernet_forward(points, normals, view_dirs, feature_vectors, self.packed_weights(),
+                                         ratio_to_weights(self.multires_v, ratio), self.mlp_mode)
+        self.last_path = "autograd-composite"
         if self.embedv_fn is not None:
             view_dirs = self.embedv_fn(view_dirs, ratio_to_weights(self.multires_v, ratio))
         if self.embedn_fn is not None:

@@ -422,6 +422,42 @@ def deformer_forward(ps, conds, packed, pe_w, batch_inds=None, points_per_frame=
     return tr, off, posed
 
 
+RENDERNET_LAYER_SHAPES = [(512, 289), (512, 512), (512, 512), (512, 512), (3, 512)]
+
+
+def rendernet_pack_weights(Ws, bs):
+    """Effective colour-network weights (weight norm already applied) -> packed fp16 hi/lo panels."""
+    dev = Ws[0].device
+    for (o, i), W, b in zip(RENDERNET_LAYER_SHAPES, Ws, bs):
+        if tuple(W.shape) != (o, i) or tuple(b.shape) != (o,):
+            raise RuntimeError(f"unexpected colour-network layer shape {tuple(W.shape)} (want {(o, i)})")
+    W_all = torch.cat([W.detach().reshape(-1).float() for W in Ws]).contiguous()
+    b_all = torch.cat([b.detach().reshape(-1).float() for b in bs]).contiguous()
+    lib = _lib.load()
+    packed = _aligned_blob(lib.recmv_rendernet_packed_bytes(), dev)
+    with torch.cuda.device(dev):
+        check(lib.recmv_rendernet_pack_weights(_ptr(W_all), _ptr(b_all), _ptr(packed), _stream(W_all)),
+              "recmv_rendernet_pack_weights")
+    return packed
+
+
+def rendernet_forward(points, normals, view_dirs, feats, packed, pe_w8, mode=None):
+    """Fused colour MLP: [P,3] x3 + [P,256] -> rgb [P,3] (tanh)."""
+    mode = DEFAULT_MLP_MODE if mode is None else mode
+    args = [t.contiguous().float() for t in (points, normals, view_dirs, feats)]
+    for t, n in zip(args, ("points", "normals", "view_dirs", "feature_vectors")):
+        _check_input(t, n)
+    P = args[0].shape[0]
+    if args[3].shape != (P, 256) or any(a.shape != (P, 3) for a in args[:3]):
+        raise RuntimeError("rendernet_forward: expected [P,3] x3 and [P,256]")
+    out = torch.empty((P, 3), dtype=torch.float32, device=args[0].device)
+    pe = (c_float * 8)(*[float(w) for w in pe_w8])
+    with torch.cuda.device(out.device):
+        check(_lib.load().recmv_rendernet_fwd(*[_ptr(a) for a in args], _ptr(packed), pe, _ptr(out), P, mode,
+                                              _stream(out)), "recmv_rendernet_fwd")
+    return out
+
+
 def make_raymarch(cam_pos, t_near, t_far, samples):
     rm = RayMarch()
     rm.cam_pos = (c_float * 3)(*[float(c) for c in cam_pos])

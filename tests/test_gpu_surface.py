@@ -135,3 +135,29 @@ def test_fused_translator_and_deformer_match_reference():
     print(f"composite deformer: {norm_err(ds, ts['ds']):.2e}")
     assert norm_err(ds, ts["ds"]) < 1e-4
     ops.check_async_errors()
+
+
+def test_fused_rendernet_matches_reference():
+    """A8: the colour MLP in one tcgen05 launch vs the golden of the reference class (same seeds => same params),
+    plus a ragged size (not a multiple of the 128-row tile) against the torch composite on the same module."""
+    from recmv_b200 import testing
+    g = load_golden("rendernet.npz")
+    torch.manual_seed(2)
+    rn = M.RenderingNetwork_view_norm(256, d_in=9, d_out=3, dims=[512] * 4, mode="idr", weight_norm=True,
+                                      multires_v=4, multires_n=0)
+    testing.perturb_module(rn, 303)
+    rn = rn.to(DEV)
+    t = {k: torch.from_numpy(g[k]).to(DEV) for k in ("points", "normals", "view_dirs", "feats", "out")}
+    with torch.no_grad():
+        col = rn(t["points"], t["normals"], t["view_dirs"], t["feats"], {"renderRatio": 0.8})
+    assert rn.last_path == "fused"
+    err = (col - t["out"]).abs().max().item()
+    print(f"rendernet fused vs reference golden: max abs err {err:.2e} (outputs in [-1,1])")
+    assert err < 1e-4
+    n = 777
+    with torch.no_grad():
+        a = rn(t["points"][:n], t["normals"][:n], t["view_dirs"][:n], t["feats"][:n], {"renderRatio": None})
+        rn.mlp_mode = _lib.MLP_FP32_SIMT   # no SIMT colour kernel: selects the torch composite
+        b = rn(t["points"][:n], t["normals"][:n], t["view_dirs"][:n], t["feats"][:n], {"renderRatio": None})
+    assert rn.last_path == "autograd-composite" and (a - b).abs().max().item() < 1e-4
+    ops.check_async_errors()
