@@ -162,6 +162,17 @@ RECMV_API int recmv_deformer_fwd(const float* ps, const float* conds, const int6
                        const recmv_voxel_t* vox /*host, may be NULL*/, float* out_translated,
                        float* out_offset, float* out_posed, int64_t P, int mode, recmv_stream_t stream);
 
+/* Forward-mode variant of recmv_deformer_fwd (A7, utils/utils.py:133-156 compute_Jacobian without autograd): every
+ * point travels as 4 tile rows (value + 3 tangents); out_jac [P,9] row-major, J[i][j] = d out_i / d p_j where
+ * `out` is out_posed when the skeleton/voxel are given, else out_translated.  The skinning weights' own
+ * dependence on the point (d w / d q, sampler backward semantics incl. zero gradient on clamped axes) is included. */
+RECMV_API int recmv_deformer_fwd_jac(const float* ps, const float* conds, const int64_t* batch_inds,
+                           int64_t points_per_frame, int num_frames, const void* packed,
+                           const float* pe_w /*host*/, const float* A, const float* trans,
+                           const recmv_voxel_t* vox /*host, may be NULL*/, float* out_translated,
+                           float* out_offset, float* out_posed, float* out_jac, int64_t P, int mode,
+                           recmv_stream_t stream);
+
 /* ---- A8: RenderingNetwork_view_norm.forward, mode 'idr' (model/RenderNet.py:59-96) in one launch -----------------
  * cat[points 3 | PE4(view_dirs) 27 | normals 3 | feature_vectors 256] = 289 -> 512 x4 ReLU -> 3 -> tanh.
  * pack: effective (weight-norm materialised) W_l [out,in] row-major fp32 concatenated, l = 0..4; b likewise.

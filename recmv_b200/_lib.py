@@ -67,6 +67,9 @@ SIGNATURES = {
     "recmv_deformer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, POINTER(c_float),
                                    c_void_p, c_void_p, POINTER(Voxel), c_void_p, c_void_p, c_void_p, c_int64,
                                    c_int, c_void_p]),
+    "recmv_deformer_fwd_jac": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, POINTER(c_float),
+                                       c_void_p, c_void_p, POINTER(Voxel), c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int, c_void_p]),
     "recmv_rendernet_packed_bytes": (c_size_t, []),
     "recmv_rendernet_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "recmv_rendernet_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p, c_int64,

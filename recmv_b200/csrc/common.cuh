@@ -179,6 +179,75 @@ __device__ __forceinline__ bool inverse_lbs_point(const Voxel& v, const float* _
   return ok;
 }
 
+// LBS forward of one canonical point WITH its Jacobian: x' = T(w(q)) [q;1] + trans and
+//   d x'_i / d q_j = T_ij + sum_bones (A_b [q;1])_i * d w_b / d q_j
+// (the weights are sampled at q itself, LBSkinner.forward, model/Deformer.py:406-445; d w / d q follows the
+// sampler's backward, GridSamplerMineKernel.cu:42-59,330-520: factor size/2 * 2/extend per axis, zero on an axis
+// whose coordinate was clamped).  Evaluated corner by corner -- T_c = sum_b ws[corner][b] A_b, Y_c = T_c [q;1] --
+// so nothing of size 24 x 3 is ever live in registers.
+__device__ __forceinline__ void lbs_forward_jac(const Voxel& v, const float* __restrict__ Af,
+                                                const float* __restrict__ tf, float qx, float qy, float qz,
+                                                float out[3], float J[9]) {
+  float gx = (qx - v.cx) / v.ext * 2.f;
+  float gy = (qy - v.cy) / v.ext * 2.f;
+  float gz = (qz - v.cz) / v.ext * 2.f;
+  float mx, my, mz;
+  float ix = clip_grad<float>(unnormalize(gx, v.W), v.W, &mx);
+  float iy = clip_grad<float>(unnormalize(gy, v.H), v.H, &my);
+  float iz = clip_grad<float>(unnormalize(gz, v.D), v.D, &mz);
+  if (!(ix == ix)) { ix = 0.f; mx = 0.f; }
+  if (!(iy == iy)) { iy = 0.f; my = 0.f; }
+  if (!(iz == iz)) { iz = 0.f; mz = 0.f; }
+  mx *= (float)v.W / v.ext; my *= (float)v.H / v.ext; mz *= (float)v.D / v.ext;   // d i / d q
+  int x0 = (int)floorf(ix), y0 = (int)floorf(iy), z0 = (int)floorf(iz);
+  int x1 = min(x0 + 1, v.W - 1), y1 = min(y0 + 1, v.H - 1), z1 = min(z0 + 1, v.D - 1);
+  const float wx[2] = {(float)(x0 + 1) - ix, ix - (float)x0};
+  const float wy[2] = {(float)(y0 + 1) - iy, iy - (float)y0};
+  const float wz[2] = {(float)(z0 + 1) - iz, iz - (float)z0};
+  const int xs[2] = {x0, x1}, ys[2] = {y0, y1}, zs[2] = {z0, z1};
+  float T[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) T[e] = 0.f;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) J[e] = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+    const float* wsp = v.ws + (((size_t)zs[dz] * v.H + ys[dy]) * v.W + xs[dx]) * 24;
+    float Tc[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) Tc[e] = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < 24; ++b) {
+      const float wb = __ldg(wsp + b);
+      const float4* a = reinterpret_cast<const float4*>(Af + b * 16);
+      const float4 r0 = __ldg(a), r1 = __ldg(a + 1), r2 = __ldg(a + 2);
+      Tc[0] = fmaf(wb, r0.x, Tc[0]); Tc[1] = fmaf(wb, r0.y, Tc[1]); Tc[2] = fmaf(wb, r0.z, Tc[2]); Tc[3] = fmaf(wb, r0.w, Tc[3]);
+      Tc[4] = fmaf(wb, r1.x, Tc[4]); Tc[5] = fmaf(wb, r1.y, Tc[5]); Tc[6] = fmaf(wb, r1.z, Tc[6]); Tc[7] = fmaf(wb, r1.w, Tc[7]);
+      Tc[8] = fmaf(wb, r2.x, Tc[8]); Tc[9] = fmaf(wb, r2.y, Tc[9]); Tc[10] = fmaf(wb, r2.z, Tc[10]); Tc[11] = fmaf(wb, r2.w, Tc[11]);
+    }
+    const float cw = wx[dx] * wy[dy] * wz[dz];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) T[e] = fmaf(cw, Tc[e], T[e]);
+    const float Y[3] = {Tc[0] * qx + Tc[1] * qy + Tc[2] * qz + Tc[3], Tc[4] * qx + Tc[5] * qy + Tc[6] * qz + Tc[7],
+                        Tc[8] * qx + Tc[9] * qy + Tc[10] * qz + Tc[11]};
+    const float dcx = (dx ? 1.f : -1.f) * wy[dy] * wz[dz] * mx;
+    const float dcy = (dy ? 1.f : -1.f) * wx[dx] * wz[dz] * my;
+    const float dcz = (dz ? 1.f : -1.f) * wx[dx] * wy[dy] * mz;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      J[3 * i + 0] = fmaf(Y[i], dcx, J[3 * i + 0]);
+      J[3 * i + 1] = fmaf(Y[i], dcy, J[3 * i + 1]);
+      J[3 * i + 2] = fmaf(Y[i], dcz, J[3 * i + 2]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    out[i] = (T[4 * i] * qx + T[4 * i + 1] * qy + T[4 * i + 2] * qz + T[4 * i + 3]) + __ldg(tf + i);
+    J[3 * i + 0] += T[4 * i + 0]; J[3 * i + 1] += T[4 * i + 1]; J[3 * i + 2] += T[4 * i + 2];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // SDF network geometry (model/network.py:135-141 getTmpSdf)
 // ------------------------------------------------------------------------------------------

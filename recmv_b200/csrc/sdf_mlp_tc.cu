@@ -92,6 +92,7 @@ struct TcParams {
   float* out_translated;         // [P,3]  p + delta
   float* out_offset;             // [P,3]  delta (MLPTranslator.offset), optional
   float* out_posed;              // [P,3]  LBS(p + delta), optional
+  float* out_jac;                // [P,9]  forward-mode variant: d out / d p (row i = gradient of output i)
   // colour network (kNet == 2): cat[p, PE4(view), n, feat] = 289 -> 512 x4 (ReLU) -> 3 -> tanh; src.x = points
   const float* normals;          // [P,3]
   const float* view_dirs;        // [P,3]
@@ -144,6 +145,24 @@ __device__ __forceinline__ float act_jvp(float z_own, float z_val, bool is_value
   return is_value ? sp : z_own * sig;
 }
 
+// tangent row j of the forward-mode variants: d PE / d x_j  (x -> e_j ; w sin(f x_c) -> w f cos(f x_c) [c == j] ;
+// w cos(f x_c) -> -w f sin(f x_c) [c == j])
+__device__ __forceinline__ void positional_encode_tangent(float cx, float cy, float cz, int j, const float* pw, float* pe) {
+  const float xj = j == 0 ? cx : (j == 1 ? cy : cz);
+#pragma unroll
+  for (int e = 0; e < 39; ++e) pe[e] = 0.f;
+  pe[j] = 1.f;
+  float f = 1.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    float sn, cs;
+    sincosf(xj * f, &sn, &cs);
+    pe[3 + 6 * k + j] = pw[2 * k] * f * cs;
+    pe[3 + 6 * k + 3 + j] = -pw[2 * k + 1] * f * sn;
+    f *= 2.f;
+  }
+}
+
 // Network descriptions driving the same pipeline.
 template <int kNet> struct Net;
 // SDF network (model/network.py:135-141): PE block -> 512 x3 -> 473 -> [skip: +PE block] 512 x4 -> 257
@@ -186,7 +205,7 @@ __global__ void __cluster_dims__(2 * kPairs, 1, 1) __launch_bounds__(kThreads, 1
 sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   using NetT = Net<kNet>;
   constexpr int kNumLayers = NetT::kLayers;   // shadows the SDF constant of common.cuh
-  static_assert(!kJvp || kNet == 0, "the forward-mode variant exists for the SDF network");
+  static_assert(!kJvp || kNet == 0 || kNet == 1, "the forward-mode variant exists for the SDF network and the deformer");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -476,7 +495,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                   for (int e = 0; e < 8; ++e) {
                     const float z_own = is_value ? v[e] : __uint_as_float(r[8 * j + e]) * kAccUnscale;  // tangents: no bias
                     const float z_val = __shfl_sync(0xffffffffu, z_own, lane & ~3);  // the point's value row
-                    v[e] = act_jvp(z_own, z_val, is_value) * kActScale;
+                    v[e] = (kNet == 0 ? act_jvp(z_own, z_val, is_value) : (z_val > 0.f ? z_own : 0.f)) * kActScale;
                   }
                 } else {
 #pragma unroll
@@ -525,7 +544,41 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
               }
             } else if (kNet == 1) {
               // deformer: columns 0..2 of the tail tile = offset; out = p + offset, then LBS forward
-              if (p < prm.P && half == 0 && c0 == 0) {
+              if (kJvp) {
+                if (half == 0 && c0 == 0) {   // warp-uniform; rows 4i..4i+3 = (value, d/dx, d/dy, d/dz) in adjacent lanes
+                  float dv[3], dt[9];         // offset and d offset_c / d p_j
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) {
+                    const float own = __uint_as_float(r[c]) * kAccUnscale;
+                    dv[c] = own + __ldg(bias + c);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) dt[3 * c + j] = __shfl_sync(0xffffffffu, own, (lane & ~3) + 1 + j);
+                  }
+                  if (is_value && p < prm.P) {
+                    const float x = __ldg(prm.src.x + 3 * p), y = __ldg(prm.src.x + 3 * p + 1), z = __ldg(prm.src.x + 3 * p + 2);
+                    const float tx = x + dv[0], ty = y + dv[1], tz = z + dv[2];
+                    dt[0] += 1.f; dt[4] += 1.f; dt[8] += 1.f;   // d (p + offset) / d p
+                    if (prm.out_translated) { prm.out_translated[3 * p] = tx; prm.out_translated[3 * p + 1] = ty; prm.out_translated[3 * p + 2] = tz; }
+                    if (prm.out_offset) { prm.out_offset[3 * p] = dv[0]; prm.out_offset[3 * p + 1] = dv[1]; prm.out_offset[3 * p + 2] = dv[2]; }
+                    if (prm.out_posed) {
+                      long long f = prm.batch_inds ? prm.batch_inds[p] : (prm.points_per_frame > 0 ? p / prm.points_per_frame : 0);
+                      f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
+                      float o[3], Jl[9];
+                      lbs_forward_jac(prm.vox, prm.bones + (size_t)f * 384, prm.trans + 3 * f, tx, ty, tz, o, Jl);
+#pragma unroll
+                      for (int i = 0; i < 3; ++i) {
+                        prm.out_posed[3 * p + i] = o[i];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                          prm.out_jac[9 * p + 3 * i + j] = Jl[3 * i] * dt[j] + Jl[3 * i + 1] * dt[3 + j] + Jl[3 * i + 2] * dt[6 + j];
+                      }
+                    } else {
+#pragma unroll
+                      for (int e = 0; e < 9; ++e) prm.out_jac[9 * p + e] = dt[e];
+                    }
+                  }
+                }
+              } else if (p < prm.P && half == 0 && c0 == 0) {
                 const float dx = fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias + 0));
                 const float dy = fmaf(__uint_as_float(r[1]), kAccUnscale, __ldg(bias + 1));
                 const float dz = fmaf(__uint_as_float(r[2]), kAccUnscale, __ldg(bias + 2));
@@ -630,14 +683,18 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         for (int e = 0; e < 192; ++e) in[e] = 0.f;
         if (p < prm.P) {
           const float x = __ldg(prm.src.x + 3 * p), y = __ldg(prm.src.x + 3 * p + 1), z = __ldg(prm.src.x + 3 * p + 2);
-          positional_encode(x, y, z, prm.pw.w, in);
-          long long f = prm.batch_inds ? prm.batch_inds[p] : (prm.points_per_frame > 0 ? p / prm.points_per_frame : 0);
-          f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
-          const float4* c = reinterpret_cast<const float4*>(prm.conds + (size_t)f * 128);
+          if (!kJvp || (row & 3) == 0) {
+            positional_encode(x, y, z, prm.pw.w, in);
+            long long f = prm.batch_inds ? prm.batch_inds[p] : (prm.points_per_frame > 0 ? p / prm.points_per_frame : 0);
+            f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
+            const float4* c = reinterpret_cast<const float4*>(prm.conds + (size_t)f * 128);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float4 t = __ldg(c + e);
-            in[39 + 4 * e] = t.x; in[40 + 4 * e] = t.y; in[41 + 4 * e] = t.z; in[42 + 4 * e] = t.w;
+            for (int e = 0; e < 32; ++e) {
+              const float4 t = __ldg(c + e);
+              in[39 + 4 * e] = t.x; in[40 + 4 * e] = t.y; in[41 + 4 * e] = t.z; in[42 + 4 * e] = t.w;
+            }
+          } else {
+            positional_encode_tangent(x, y, z, (row & 3) - 1, prm.pw.w, in);   // the condition does not depend on p
           }
 #pragma unroll
           for (int e = 0; e < 167; ++e) in[e] *= kActScale;
@@ -659,21 +716,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         if (!kJvp || (row & 3) == 0) {
           positional_encode(cx, cy, cz, prm.pw.w, pe);
         } else {
-          // tangent row j: d PE / d x_j  (x -> e_j ; w sin(f x_c) -> w f cos(f x_c) [c == j] ; cos -> -w f sin)
-          const int j = (row & 3) - 1;
-          const float xj = j == 0 ? cx : (j == 1 ? cy : cz);
-#pragma unroll
-          for (int e = 0; e < 39; ++e) pe[e] = 0.f;
-          pe[j] = 1.f;
-          float f = 1.f;
-#pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            float sn, cs;
-            sincosf(xj * f, &sn, &cs);
-            pe[3 + 6 * k + j] = prm.pw.w[2 * k] * f * cs;
-            pe[3 + 6 * k + 3 + j] = -prm.pw.w[2 * k + 1] * f * sn;
-            f *= 2.f;
-          }
+          positional_encode_tangent(cx, cy, cz, (row & 3) - 1, prm.pw.w, pe);
         }
 #pragma unroll
         for (int e = 0; e < 39; ++e) pe[e] *= kActScale;
@@ -736,6 +779,7 @@ int tc_prepare_launch(int dev) {
   cudaError_t e = cudaFuncSetAttribute(sdf_tc_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return (int)e;
   done[dev & 15] = true;
@@ -889,10 +933,33 @@ extern "C" int recmv_translator_pack_weights(const float* W_all, const float* b_
   return RECMV_OK;
 }
 
+static int deformer_launch(const float* ps, const float* conds, const int64_t* batch_inds, int64_t points_per_frame,
+                           int num_frames, const void* packed, const float* pe_w, const float* A, const float* trans,
+                           const recmv_voxel_t* vox, float* out_translated, float* out_offset, float* out_posed,
+                           float* out_jac, int64_t P, int mode, recmv_stream_t stream);
+
+extern "C" int recmv_deformer_fwd_jac(const float* ps, const float* conds, const int64_t* batch_inds,
+                                      int64_t points_per_frame, int num_frames, const void* packed, const float* pe_w,
+                                      const float* A, const float* trans, const recmv_voxel_t* vox, float* out_translated,
+                                      float* out_offset, float* out_posed, float* out_jac, int64_t P, int mode,
+                                      recmv_stream_t stream) {
+  if (!out_jac) return RECMV_E_NULL;
+  return deformer_launch(ps, conds, batch_inds, points_per_frame, num_frames, packed, pe_w, A, trans, vox, out_translated,
+                         out_offset, out_posed, out_jac, P, mode, stream);
+}
+
 extern "C" int recmv_deformer_fwd(const float* ps, const float* conds, const int64_t* batch_inds,
                                   int64_t points_per_frame, int num_frames, const void* packed, const float* pe_w,
                                   const float* A, const float* trans, const recmv_voxel_t* vox, float* out_translated,
                                   float* out_offset, float* out_posed, int64_t P, int mode, recmv_stream_t stream) {
+  return deformer_launch(ps, conds, batch_inds, points_per_frame, num_frames, packed, pe_w, A, trans, vox, out_translated,
+                         out_offset, out_posed, nullptr, P, mode, stream);
+}
+
+static int deformer_launch(const float* ps, const float* conds, const int64_t* batch_inds, int64_t points_per_frame,
+                           int num_frames, const void* packed, const float* pe_w, const float* A, const float* trans,
+                           const recmv_voxel_t* vox, float* out_translated, float* out_offset, float* out_posed,
+                           float* out_jac, int64_t P, int mode, recmv_stream_t stream) {
   if (P < 0 || num_frames <= 0) return RECMV_E_SHAPE;
   if (P == 0) return RECMV_OK;
   if (!ps || !conds || !packed || !pe_w) return RECMV_E_NULL;
@@ -923,12 +990,16 @@ extern "C" int recmv_deformer_fwd(const float* ps, const float* conds, const int
   prm.conds = conds; prm.batch_inds = (const long long*)batch_inds; prm.points_per_frame = points_per_frame;
   prm.num_frames = num_frames; prm.bones = A; prm.trans = trans;
   if (vox) prm.vox = to_voxel(vox);
-  prm.out_translated = out_translated; prm.out_offset = out_offset; prm.out_posed = out_posed;
-  int64_t tiles = (P + 127) / 128;
+  prm.out_translated = out_translated; prm.out_offset = out_offset; prm.out_posed = out_posed; prm.out_jac = out_jac;
+  const int pts_per_tile = out_jac ? 32 : 128;   // forward mode: 4 rows per point
+  int64_t tiles = (P + pts_per_tile - 1) / pts_per_tile;
   int64_t want = (tiles + kPairs - 1) / kPairs;
   int maxc = tc_max_clusters(dev);
   int clusters = (int)(want < maxc ? want : maxc);
-  sdf_tc_kernel<false, 1><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
+  if (out_jac)
+    sdf_tc_kernel<true, 1><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
+  else
+    sdf_tc_kernel<false, 1><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
   return launch_status();
 }
 

@@ -59,7 +59,12 @@ class CompositeDeformer(nn.Module):
             out = deformer(out, cond, batch_inds, **kwargs)
         return out
 
-    def _fused_forward(self, ps, conds, batch_inds, kwargs):
+    def value_and_jacobian(self, ps, conds, batch_inds, **kwargs):
+        """(D(p) [P,3], J = dD/dp [P,3,3]) of [MLPTranslator, LBSkinner] in ONE forward-mode launch (no autograd
+        graph; utils.compute_Jacobian semantics: row i = gradient of D_i).  None when this composite is not fusable."""
+        return self._fused_forward(ps.detach(), conds, batch_inds, kwargs, want_jacobian=True)
+
+    def _fused_forward(self, ps, conds, batch_inds, kwargs, want_jacobian=False):
         """[MLPTranslator, LBSkinner] without an autograd graph -> ONE launch (translator MLP on tcgen05, then
         the skinning-voxel sample + bone blend in the same kernel's epilogue)."""
         if self.N != 2 or not isinstance(self.defs[0], MLPTranslator) or not isinstance(self.defs[1], LBSkinner):
@@ -69,20 +74,22 @@ class CompositeDeformer(nn.Module):
             return None
         poses, trans = conds[1]
         tensors = [ps, conds[0], poses, trans] + list(tr.parameters())
-        if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        if not want_jacobian and torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
             return None
         A = sk.bone_matrices(poses)
         center = sk.bbox_center.view(-1)[:3].tolist()
         extend = float(sk.bbox_extend.view(-1)[0])
         ratio = kwargs['ratio']['deformerRatio']
         ppf = 0 if batch_inds is not None else ps.shape[1]
-        _, off, posed = ops.deformer_forward(ps.reshape(-1, 3), conds[0], tr.packed_weights(),
-                                             ratio_to_weights(tr.multires, ratio), batch_inds, ppf,
-                                             (A, trans + sk.extra_trans, sk.ws_channels_last(), center, extend),
-                                             tr.mlp_mode, want_offset=True, want_translated=False)
-        tr.offset[kwargs['offset_type']] = off if batch_inds is not None else off.view(ps.shape[0], ps.shape[1], 3)
-        tr.last_path = sk.last_path = "fused-deformer"
-        return posed if batch_inds is not None else posed.view(ps.shape)
+        res = ops.deformer_forward(ps.reshape(-1, 3), conds[0], tr.packed_weights(),
+                                   ratio_to_weights(tr.multires, ratio), batch_inds, ppf,
+                                   (A, trans + sk.extra_trans, sk.ws_channels_last(), center, extend),
+                                   tr.mlp_mode, want_offset=True, want_translated=False, want_jacobian=want_jacobian)
+        off, posed = res[1], res[2]
+        tr.offset[kwargs.get('offset_type')] = off if batch_inds is not None else off.view(ps.shape[0], ps.shape[1], 3)
+        tr.last_path = sk.last_path = "fused-deformer-jvp" if want_jacobian else "fused-deformer"
+        posed = posed if batch_inds is not None else posed.view(ps.shape)
+        return (posed, res[3]) if want_jacobian else posed
 
 
 class MLPTranslator(nn.Module):

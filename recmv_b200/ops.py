@@ -395,9 +395,10 @@ def translator_pack_weights(Ws, bs):
 
 
 def deformer_forward(ps, conds, packed, pe_w, batch_inds=None, points_per_frame=0, skin=None, mode=None,
-                     want_offset=True, want_translated=True):
+                     want_offset=True, want_translated=True, want_jacobian=False):
     """MLPTranslator (+ LBS forward when skin = (A, trans, ws_cl, center, extend)) in one fused launch.
-    Returns (translated [P,3] or None, offset [P,3] or None, posed [P,3] or None)."""
+    Returns (translated [P,3] or None, offset [P,3] or None, posed [P,3] or None) -- plus the Jacobian [P,3,3]
+    of the last stage w.r.t. ps (forward-mode launch) when want_jacobian."""
     mode = DEFAULT_MLP_MODE if mode is None else mode
     ps = ps.contiguous().float()
     _check_input(ps, "ps")
@@ -415,6 +416,13 @@ def deformer_forward(ps, conds, packed, pe_w, batch_inds=None, points_per_frame=
     if batch_inds is not None:
         batch_inds = batch_inds.contiguous().long()
     with torch.cuda.device(dev):
+        if want_jacobian:
+            jac = torch.empty((P, 3, 3), dtype=torch.float32, device=dev)
+            check(_lib.load().recmv_deformer_fwd_jac(_ptr(ps), _ptr(conds), _ptr(batch_inds), int(points_per_frame),
+                                                     int(conds.shape[0]), _ptr(packed), _pe_array(pe_w), _ptr(A),
+                                                     _ptr(trans), vox, _ptr(tr), _ptr(off), _ptr(posed), _ptr(jac), P,
+                                                     mode, _stream(ps)), "recmv_deformer_fwd_jac")
+            return tr, off, posed, jac
         check(_lib.load().recmv_deformer_fwd(_ptr(ps), _ptr(conds), _ptr(batch_inds), int(points_per_frame),
                                              int(conds.shape[0]), _ptr(packed), _pe_array(pe_w), _ptr(A), _ptr(trans),
                                              vox, _ptr(tr), _ptr(off), _ptr(posed), P, mode, _stream(ps)),

@@ -40,8 +40,9 @@ def _angle_ok(direct, rays, athreshold):
 
 
 def _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2,
-           times):
-    """deform(ps, inds) -> posed points.  Mutates and returns initTmpPs like the reference."""
+           times, deform_jac=None):
+    """deform(ps, inds) -> posed points; deform_jac(ps, inds) -> (posed, J [P,3,3]) or None (fused forward-mode
+    launch).  Mutates and returns initTmpPs like the reference."""
     cam = cam_pos.view(1, 3)
     with torch.no_grad():
         check = (tmpSdf(initTmpPs, ratio).view(-1).abs() < dthreshold) & \
@@ -59,11 +60,20 @@ def _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthresho
             loss1 = f.abs().view(-1)
         else:
             loss1 = tmpSdf(cur, ratio).abs().view(-1)
-        direct = deform(cur, batch_inds[sel]) - cam
+        dj = deform_jac(cur.detach(), batch_inds[sel]) if (fused and deform_jac is not None) else None
+        if dj is not None:
+            # no autograd through the deformer: loss2 depends on p only through D(p), so grad_p = J^T dloss2/dD
+            direct = (dj[0] - cam).detach().requires_grad_(True)
+        else:
+            direct = deform(cur, batch_inds[sel]) - cam
         up = torch.cross(direct, rays[sel], dim=1)
         loss2 = (up.norm(dim=1) / direct.norm(dim=1)).abs()
         loss = w1 * loss1 + w2 * loss2
-        if fused:
+        if dj is not None:
+            gd = torch.autograd.grad((w2 * loss2).sum(), direct)[0]
+            grad = torch.bmm(dj[1].transpose(1, 2), gd.unsqueeze(-1)).squeeze(-1) + w1 * torch.sign(f) * gf
+            loss = loss.detach()
+        elif fused:
             grad = torch.autograd.grad((w2 * loss2).sum(), cur, retain_graph=False, create_graph=False)[0]
             grad = grad + w1 * torch.sign(f) * gf
             loss = loss.detach()
@@ -79,18 +89,34 @@ def _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthresho
     return initTmpPs.detach(), ~unfinished
 
 
+def _jac_fn(deformer, conds_fn, ratio, offset_type):
+    """(ps, inds) -> (D(ps), dD/dps) through the deformer's fused forward-mode launch, or None if it has none."""
+    fn = getattr(deformer, "value_and_jacobian", None)
+    if fn is None:
+        return None
+
+    def deform_jac(ps, inds):
+        if not ps.is_cuda:
+            return None
+        with torch.no_grad():
+            return fn(ps, conds_fn(), inds, ratio=ratio, offset_type=offset_type)
+    return deform_jac
+
+
 def OptimizeSurfacePs(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deformer, defconds,
                       dthreshold=5.e-5, athreshold=0.02, w1=3.05, w2=1., times=5):
     def deform(ps, inds):
         return deformer(ps, defconds, inds, ratio=ratio)
-    return _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2, times)
+    return _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2, times,
+                  _jac_fn(deformer, lambda: defconds, ratio, None))
 
 
 def OptimizeGarmentSurfaceSinlge(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deformer, defconds,
                                  dthreshold=5.e-5, athreshold=0.02, w1=3.05, w2=1., times=5, offset_type=None):
     def deform(ps, inds):
         return deformer(ps, defconds, inds, ratio=ratio, offset_type=offset_type)
-    return _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2, times)
+    return _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2, times,
+                  _jac_fn(deformer, lambda: defconds, ratio, offset_type))
 
 
 def OptimizeGarmentSurfacePs(cam_pos, rays_list, initTmpPs_list, batch_inds_list, tmpSdf_nets, ratio, deformer,
@@ -102,7 +128,8 @@ def OptimizeGarmentSurfacePs(cam_pos, rays_list, initTmpPs_list, batch_inds_list
                                                             rays_list, garment_names)):
         def deform(p, i, dcond=dcond, name=name):
             return deformer(p, [dcond, smpl_conds], i, ratio=ratio, offset_type=name)
-        p, ok = _solve(cam_pos, rays, ps, inds, tmpSdf_nets[gi], ratio, deform, dthreshold, athreshold, w1, w2, times)
+        p, ok = _solve(cam_pos, rays, ps, inds, tmpSdf_nets[gi], ratio, deform, dthreshold, athreshold, w1, w2, times,
+                       _jac_fn(deformer, lambda dcond=dcond: [dcond, smpl_conds], ratio, name))
         out_ps.append(p)
         out_ok.append(ok)
     return out_ps, out_ok

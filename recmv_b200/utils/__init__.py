@@ -25,11 +25,22 @@ def _deform(deformer, ps, defconds, batch_inds, ratio, offset_type):
     return deformer(ps, defconds, batch_inds, ratio=ratio, offset_type=offset_type)
 
 
+def _value_and_jacobian(deformer, ps, defconds, batch_inds, ratio, offset_type, check):
+    """(D(p), J): one forward-mode launch of the fused deformer when no graph is kept (phase != train) and the
+    composite is fusable; otherwise the reference's three autograd passes."""
+    if not check and hasattr(deformer, "value_and_jacobian") and ps.is_cuda:
+        with torch.no_grad():
+            res = deformer.value_and_jacobian(ps, defconds, batch_inds, ratio=ratio, offset_type=offset_type)
+        if res is not None:
+            return res
+    ds = _deform(deformer, ps, defconds, batch_inds, ratio, offset_type)
+    return ds, compute_Jacobian(ps, ds, check, check)
+
+
 def compute_cardinal_rays(deformer, ps, rays, defconds, batch_inds, ratio, phase, offset_type=None):
     """crays = normalize(J^-1 v) with the FastMinv singularity fallback (utils/utils.py:232-250)."""
     check = phase in ('train', 'Train')
-    ds = _deform(deformer, ps, defconds, batch_inds, ratio, offset_type)
-    J = compute_Jacobian(ps, ds, check, check)
+    ds, J = _value_and_jacobian(deformer, ps, defconds, batch_inds, ratio, offset_type, check)
     Jinv, ok = FastDiff3x3MinvFunction.apply(J)
     crays = Jinv.matmul(rays.view(-1, 3, 1)).view(-1, 3)
     bad = ~ok
@@ -48,8 +59,7 @@ def compute_deformed_normals(sdf, deformer, ps, defconds, batch_inds, ratio, pha
     sdfs = sdf(ps, ratio)
     check = phase in ('train', 'Train')
     onx = torch.autograd.grad(sdfs, ps, torch.ones_like(sdfs), retain_graph=check, create_graph=check)[0]
-    ds = _deform(deformer, ps, defconds, batch_inds, ratio, offset_type)
-    J = compute_Jacobian(ps, ds, check, check)
+    ds, J = _value_and_jacobian(deformer, ps, defconds, batch_inds, ratio, offset_type, check)
     Jinv, ok = FastDiff3x3MinvFunction.apply(J)
     nx = Jinv.transpose(-2, -1).matmul(onx.view(-1, 3, 1)).view(-1, 3)
     bad = ~ok

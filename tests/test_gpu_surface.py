@@ -161,3 +161,30 @@ def test_fused_rendernet_matches_reference():
         b = rn(t["points"][:n], t["normals"][:n], t["view_dirs"][:n], t["feats"][:n], {"renderRatio": None})
     assert rn.last_path == "autograd-composite" and norm_err(a, b) < 1e-4
     ops.check_async_errors()
+
+
+def test_fused_deformer_jacobian_matches_autograd():
+    """A7: D(p) and J = dD/dp from ONE forward-mode launch of the fused deformer vs three autograd passes through
+    the torch translator + CUDA sampler (utils.compute_Jacobian, the reference's procedure); then the reference
+    goldens of the quantities built from J (cardinal rays, deformed normals) through the fused path."""
+    g = load_golden("surface.npz")
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in g.items()}
+    sdf, deformer = _scene()
+    defconds = [t["conds"], [t["poses"], t["trans"]]]
+    with torch.no_grad():
+        ds, J = deformer.value_and_jacobian(t["ps"], defconds, t["batch_inds"], ratio=RATIO, offset_type="body")
+    assert deformer.defs[0].last_path == "fused-deformer-jvp"
+    pts = t["ps"].clone().requires_grad_(True)
+    ds_ref = deformer(pts, defconds, t["batch_inds"], ratio=RATIO, offset_type="body")
+    assert deformer.defs[0].last_path == "autograd-composite"
+    J_ref = U.compute_Jacobian(pts, ds_ref, False, False)
+    print(f"fused deformer JVP: ds {norm_err(ds, ds_ref):.2e}  J {norm_err(J, J_ref):.2e}")
+    assert norm_err(ds, t["ds"]) < 1e-4 and norm_err(J, J_ref) < 2e-4
+    crays, ds2 = U.compute_cardinal_rays(deformer, t["ps"].clone().requires_grad_(True), t["rays"], defconds,
+                                         t["batch_inds"], RATIO, "test", "body")
+    assert deformer.defs[0].last_path == "fused-deformer-jvp"
+    assert norm_err(ds2, t["ds"]) < 1e-4 and (crays - t["crays"]).abs().max() < 2e-4
+    nrm, _ = U.compute_deformed_normals(sdf, deformer, t["ps"].clone().requires_grad_(True), defconds,
+                                        t["batch_inds"], RATIO, "test", "body")
+    assert (nrm - t["normals"]).abs().max() < 2e-4
+    ops.check_async_errors()
