@@ -82,6 +82,43 @@ __global__ void __launch_bounds__(256) gs3d_fwd_kernel(const T* __restrict__ inp
   }
 }
 
+// fp32, channels-last, C % 4 == 0: one 128-bit load per corner and channel quad (the 24-channel skinning voxel:
+// 6 loads per corner, 3 fully used sectors), same summation order as the generic kernel.
+__global__ void __launch_bounds__(256) gs3d_fwd_cl4_kernel(const float* __restrict__ input, const float* __restrict__ grid,
+                                                           float* __restrict__ output, int N, int C, int D, int H,
+                                                           int W, int64_t P) {
+  const int64_t total = (int64_t)N * P;
+  const int Q = C >> 2;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / P);
+    const int64_t p = idx - (int64_t)n * P;
+    const float* g = grid + idx * 3;
+    const Cell<float> cl = make_cell<float>(__ldg(g), __ldg(g + 1), __ldg(g + 2), D, H, W);
+    const float4* corner[8];
+    float cw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+      const bool in = cl.inx[dx] && cl.iny[dy] && cl.inz[dz];
+      cw[k] = in ? cl.wx[dx] * cl.wy[dy] * cl.wz[dz] : 0.f;
+      corner[k] = in ? reinterpret_cast<const float4*>(input + ((((size_t)n * D + cl.z[dz]) * H + cl.y[dy]) * W + cl.x[dx]) * C)
+                     : nullptr;
+    }
+    for (int q = 0; q < Q; ++q) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (corner[k]) {
+          const float4 t = __ldg(corner[k] + q);
+          acc.x += t.x * cw[k]; acc.y += t.y * cw[k]; acc.z += t.z * cw[k]; acc.w += t.w * cw[k];
+        }
+      float* o = output + ((size_t)n * C + 4 * q) * P + p;
+      o[0] = acc.x; o[P] = acc.y; o[2 * P] = acc.z; o[3 * P] = acc.w;
+    }
+  }
+}
+
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(256) gs3d_bwd_kernel(const T* __restrict__ input,
                                                        const T* __restrict__ grid,
@@ -213,6 +250,8 @@ static int gs_dispatch_fwd(const void* input, const void* grid, void* output, in
   int g = stride_grid((int64_t)N * P, 256, 8);
   if (layout == RECMV_LAYOUT_NCDHW)
     gs3d_fwd_kernel<T, RECMV_LAYOUT_NCDHW><<<g, 256, 0, st>>>((const T*)input, (const T*)grid, (T*)output, N, C, D, H, W, P);
+  else if (sizeof(T) == 4 && (C & 3) == 0 && ((uintptr_t)input & 15) == 0)
+    gs3d_fwd_cl4_kernel<<<g, 256, 0, st>>>((const float*)input, (const float*)grid, (float*)output, N, C, D, H, W, P);
   else
     gs3d_fwd_kernel<T, RECMV_LAYOUT_NDHWC><<<g, 256, 0, st>>>((const T*)input, (const T*)grid, (T*)output, N, C, D, H, W, P);
   return launch_status();

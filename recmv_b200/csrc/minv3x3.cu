@@ -3,7 +3,7 @@
 //
 // HBM-bound: 72 B in + 37 B out per matrix (fp32).  The reference uses one thread per matrix with
 // nine strided scalar loads; here a CTA stages 256 matrices through shared memory with fully
-// coalesced 128-bit loads/stores, then each thread inverts one matrix out of shared memory
+// coalesced 128-bit loads/stores (scalar for the ragged tail), then each thread inverts one matrix out of shared memory
 // (stride 9 words => conflict-free), on the caller's stream (the reference launches on the legacy
 // default stream).
 #include "common.cuh"
@@ -12,11 +12,34 @@ namespace recmv {
 
 constexpr int kMinvThreads = 256;
 
+// Global <-> shared staging of one CTA tile (256 matrices).  Full tiles of a 16-byte aligned array move as
+// 128-bit words (a tile is 9216 / 18432 bytes, so every tile start stays aligned); the ragged last tile and
+// unaligned views fall back to scalars.
 template <typename T>
 __device__ __forceinline__ void stage_in(const T* __restrict__ g, T* s, int64_t base, int64_t n_elems) {
   // n_elems = valid scalars for this CTA (<= 256*9)
+  if (n_elems == kMinvThreads * 9 && ((uintptr_t)(g + base) & 15) == 0) {
+    const uint4* gv = reinterpret_cast<const uint4*>(g + base);
+    uint4* sv = reinterpret_cast<uint4*>(s);
+    constexpr int kVec = kMinvThreads * 9 * (int)sizeof(T) / 16;
+#pragma unroll
+    for (int i = threadIdx.x; i < kVec; i += kMinvThreads) sv[i] = __ldg(gv + i);
+    return;
+  }
   for (int i = threadIdx.x; i < kMinvThreads * 9; i += kMinvThreads)
     s[i] = (i < n_elems) ? g[base + i] : (T)0;
+}
+template <typename T>
+__device__ __forceinline__ void stage_out(T* __restrict__ g, const T* s, int64_t base, int64_t n_elems) {
+  if (n_elems == kMinvThreads * 9 && ((uintptr_t)(g + base) & 15) == 0) {
+    uint4* gv = reinterpret_cast<uint4*>(g + base);
+    const uint4* sv = reinterpret_cast<const uint4*>(s);
+    constexpr int kVec = kMinvThreads * 9 * (int)sizeof(T) / 16;
+#pragma unroll
+    for (int i = threadIdx.x; i < kVec; i += kMinvThreads) gv[i] = sv[i];
+    return;
+  }
+  for (int i = threadIdx.x; i < n_elems; i += kMinvThreads) g[base + i] = s[i];
 }
 
 template <typename T>
@@ -24,7 +47,7 @@ __global__ void __launch_bounds__(kMinvThreads) minv3x3_fwd_kernel(const T* __re
                                                                    T* __restrict__ invs,
                                                                    uint8_t* __restrict__ ok,
                                                                    int64_t n) {
-  __shared__ T s[kMinvThreads * 9];
+  __shared__ __align__(16) T s[kMinvThreads * 9];
   for (int64_t blk = blockIdx.x; blk * kMinvThreads < n; blk += gridDim.x) {
     int64_t m0 = blk * kMinvThreads;
     int64_t cnt = min((int64_t)kMinvThreads, n - m0);
@@ -39,7 +62,7 @@ __global__ void __launch_bounds__(kMinvThreads) minv3x3_fwd_kernel(const T* __re
     for (int i = 0; i < 9; ++i) s[threadIdx.x * 9 + i] = inv[i];
     if (threadIdx.x < cnt) ok[m0 + threadIdx.x] = good ? 1 : 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt * 9; i += kMinvThreads) invs[m0 * 9 + i] = s[i];
+    stage_out(invs, s, m0 * 9, cnt * 9);
     __syncthreads();
   }
 }
@@ -49,8 +72,8 @@ template <typename T>
 __global__ void __launch_bounds__(kMinvThreads) minv3x3_bwd_kernel(const T* __restrict__ grads,
                                                                    const T* __restrict__ invs,
                                                                    T* __restrict__ outs, int64_t n) {
-  __shared__ T sg[kMinvThreads * 9];
-  __shared__ T si[kMinvThreads * 9];
+  __shared__ __align__(16) T sg[kMinvThreads * 9];
+  __shared__ __align__(16) T si[kMinvThreads * 9];
   for (int64_t blk = blockIdx.x; blk * kMinvThreads < n; blk += gridDim.x) {
     int64_t m0 = blk * kMinvThreads;
     int64_t cnt = min((int64_t)kMinvThreads, n - m0);
@@ -76,7 +99,7 @@ __global__ void __launch_bounds__(kMinvThreads) minv3x3_bwd_kernel(const T* __re
 #pragma unroll
     for (int i = 0; i < 9; ++i) sg[threadIdx.x * 9 + i] = o[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt * 9; i += kMinvThreads) outs[m0 * 9 + i] = sg[i];
+    stage_out(outs, sg, m0 * 9, cnt * 9);
     __syncthreads();
   }
 }
