@@ -43,7 +43,8 @@ constexpr int kPairs = 1;  // MMA pairs per cluster sharing every weight tile th
                            // stream in lockstep and the frame gets SLOWER (tc3 1.41 -> 1.32 M rays/s, tc1 2.36 -> 2.08);
                            // clusters of 4 also only fit on 132 of the 148 SMs.
 constexpr int kRowsPerCta = 64;
-constexpr int kSlots = 5;
+constexpr int kSlots = 5;       // weight ring slots in their own region ...
+constexpr int kSlotsMax = 9;    // ... + 4 more in the (unused) activation lo plane when a single pass is issued
 constexpr uint32_t kSlotBytes = 16384;
 // shared memory map (offsets from a 1024-aligned base)
 constexpr uint32_t kOffAHi = 0;
@@ -53,14 +54,14 @@ constexpr uint32_t kOffPeLo = 139264;
 constexpr uint32_t kOffW = 147456;
 constexpr uint32_t kOffBar = kOffW + kSlots * kSlotBytes;  // 229376
 // barrier indices (8 bytes each)
-constexpr int kBarFull = 0;      // [5] pair leader: weight slot filled (1 arming arrival + tx bytes of both CTAs)
-constexpr int kBarEmpty = 5;     // [5] cluster CTAs 0/1: slot consumed by every pair (one tcgen05.commit per pair)
-constexpr int kBarAReady = 10;   // [8] leader: activation K-block written by both CTAs (8 warp arrivals)
-constexpr int kBarPeReady = 18;  //     leader: positional-encoding block written (4 warp arrivals)
-constexpr int kBarPeFree = 19;   //     local : layer-4 MMAs done with the PE block (commit multicast)
-constexpr int kBarAccFull = 20;  // [2] local : layer accumulator complete (commit multicast)
-constexpr int kBarAccEmpty = 22; // [2] leader: accumulator drained by all 16 epilogue warps of the pair
-constexpr int kNumBars = 24;
+constexpr int kBarFull = 0;      // [9] pair leader: weight slot filled (1 arming arrival + tx bytes of both CTAs)
+constexpr int kBarEmpty = 9;     // [9] cluster CTAs 0/1: slot consumed by every pair (one tcgen05.commit per pair)
+constexpr int kBarAReady = 18;   // [8] leader: activation K-block written by both CTAs (4 * kEpiGroups warp arrivals)
+constexpr int kBarPeReady = 26;  //     leader: positional-encoding block written (4 warp arrivals)
+constexpr int kBarPeFree = 27;   //     local : layer-4 MMAs done with the PE block (commit multicast, both issuers)
+constexpr int kBarAccFull = 28;  // [2] local : layer accumulator complete (commit multicast, both issuers)
+constexpr int kBarAccEmpty = 30; // [2] leader: accumulator drained by all epilogue warps of the pair
+constexpr int kNumBars = 32;
 constexpr uint32_t kOffMisc = kOffBar + kNumBars * 8;  // tmem ptr, abort flag, valid flags
 constexpr uint32_t kSmemBytes = kOffMisc + 16 + 128 + 1024 /*alignment slack*/;
 
@@ -229,16 +230,25 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   auto tile_of = [&](long long it) { return (cluster_id + it * num_clusters) * kPairs + (long long)pair; };
   const int passes = prm.passes;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  // Single-pass mode never reads the activation lo plane, so its 64 KB can serve as four more weight slots
+  // (RECMV_TC_DEEP_RING).  Measured: 9 slots instead of 5 change nothing (tc1 2.32 vs 2.36 M rays/s) -- the weight
+  // stream is bound by L2 -> SM bandwidth (~8-9 TB/s aggregate in both modes), not by ring depth x latency.
+#ifdef RECMV_TC_DEEP_RING
+  const int nslots = passes == 1 ? kSlotsMax : kSlots;
+#else
+  const int nslots = kSlots;
+#endif
+  auto SLOT = [&](int s) { return base + (s < kSlots ? kOffW + (uint32_t)s * kSlotBytes : kOffALo + (uint32_t)(s - kSlots) * kSlotBytes); };
 
   if (threadIdx.x == 0) {
     *abort_flag = 0;
-    for (int s = 0; s < kSlots; ++s) { mbar_init(BAR(kBarFull + s), 1); mbar_init(BAR(kBarEmpty + s), kPairs); }
+    for (int s = 0; s < kSlotsMax; ++s) { mbar_init(BAR(kBarFull + s), 1); mbar_init(BAR(kBarEmpty + s), kPairs); }
     for (int k = 0; k < 8; ++k) mbar_init(BAR(kBarAReady + k), 4 * kEpiGroups);
     mbar_init(BAR(kBarPeReady), 4);
     mbar_init(BAR(kBarPeFree), 2);                               // one commit per MMA issuer
     for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 2); mbar_init(BAR(kBarAccEmpty + b), 2 * kEpiWarps); }
     // arm generation 0 of every weight slot of this pair (both CTAs' halves: 2 x 16 KB)
-    if (leader) for (int s = 0; s < kSlots; ++s) mbar_expect_tx_local(BAR(kBarFull + s), 2 * kSlotBytes);
+    if (leader) for (int s = 0; s < kSlotsMax; ++s) mbar_expect_tx_local(BAR(kBarFull + s), 2 * kSlotBytes);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) prefetch_tmap(&tmap128);
@@ -272,9 +282,9 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                 for (int plane = 0; plane < nplanes; ++plane) {
                   mbar_wait(BAR(kBarEmpty + slot), ring ^ 1u, abort_flag, prm.status, 100 + slot);
                   const int row = (plane * NetT::kPanels + NetT::pbase(l) + kbi) * 512 + nt * 256 + (int)rank * 128;
-                  tma_load_2d_pair_mcast(base + kOffW + slot * kSlotBytes, (const void*)&tmap128,
+                  tma_load_2d_pair_mcast(SLOT(slot), (const void*)&tmap128,
                                          mapa(BAR(kBarFull + slot), 0), mask, 0, row);
-                  if (++slot == kSlots) { slot = 0; ring ^= 1u; }
+                  if (++slot == nslots) { slot = 0; ring ^= 1u; }
                 }
               }
             }
@@ -293,7 +303,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
       const int my_nt = warp == 1 ? 0 : 1;
       int slot = 0;          // ring position of the next slot use in producer order
       uint32_t ring = 0;
-      auto advance = [&](int n) { slot += n; if (slot >= kSlots) { slot -= kSlots; ring ^= 1u; } };  // n < kSlots
+      auto advance = [&](int n) { slot += n; if (slot >= nslots) { slot -= nslots; ring ^= 1u; } };  // n < nslots
       // try_wait results obtained ahead of time: {barrier, parity, completed}
       uint32_t fh_bar = 0, fh_par = 0, fh_ok = 0, ah_bar = 0, ah_par = 0, ah_ok = 0;
       auto poll = [&](uint32_t bar, uint32_t par) -> uint32_t { return mbar_try_wait(bar, par) ? 1u : 0u; };
@@ -315,7 +325,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
       };
       auto poll_full_at = [&](int ahead) {   // poll the slot `ahead` uses after the current position
         int s2 = slot + ahead; uint32_t r2 = ring;
-        if (s2 >= kSlots) { s2 -= kSlots; r2 ^= 1u; }
+        if (s2 >= nslots) { s2 -= nslots; r2 ^= 1u; }
         fh_bar = BAR(kBarFull + s2); fh_par = r2; fh_ok = poll(fh_bar, r2);
       };
       const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
@@ -372,7 +382,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
               advance(my_nt * planes);                                // the lower tile's uses of this K block
               // ---- slot with w_hi ---------------------------------------------------------------------------
               wait_full(230);
-              uint64_t b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
+              uint64_t b = smem_desc_sw128(SLOT(slot));
               const int s_hi = slot;
               advance(1);
               // poll ahead: this K block's w_lo slot, or the next K block's first slot
@@ -399,7 +409,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
               // ---- slot with w_lo (parity mode; not in the hi*hi sweep) --------------------------------------
               if (planes == 2) {
                 wait_full(240);
-                b = smem_desc_sw128(base + kOffW + slot * kSlotBytes);
+                b = smem_desc_sw128(SLOT(slot));
                 const int s_lo = slot;
                 advance(1);
                 poll_full_at((T - 1) * planes);
@@ -507,7 +517,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
               const int kb = f >> 6, chunk = (f & 63) >> 3;
               const uint32_t off = (uint32_t)kb * 8192u + sw128_offset(row, chunk);
               st_shared_v4(base + kOffAHi + off, hi);
-              st_shared_v4(base + kOffALo + off, lo);
+              if (passes == 3) st_shared_v4(base + kOffALo + off, lo);
             }
             if (c == 0 && tr) TRACE(trole, it, l, 6);
             // this warp's kCw columns of K block (f0 >> 6) of the next layer's input are complete
@@ -673,7 +683,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           split8(v, hi, lo);
           const uint32_t off = (uint32_t)(chunk >> 3) * 8192u + sw128_offset(row, chunk & 7);
           st_shared_v4(base + kOffAHi + off, hi);
-          st_shared_v4(base + kOffALo + off, lo);
+          if (passes == 3) st_shared_v4(base + kOffALo + off, lo);
         }
       } else if (kNet == 1) {
         // deformer input row: [PE(p) (39) | cond[frame] (128) | 0 (25)] = three 64-wide K blocks written into the
@@ -706,7 +716,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           split8(in + 8 * chunk, hi, lo);
           const uint32_t off = (uint32_t)(chunk >> 3) * 8192u + sw128_offset(row, chunk & 7);
           st_shared_v4(base + kOffAHi + off, hi);
-          st_shared_v4(base + kOffALo + off, lo);
+          if (passes == 3) st_shared_v4(base + kOffALo + off, lo);
         }
       } else {
       float pe[40];
