@@ -158,6 +158,56 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def secondary_rates(dev, ren, mode):
+    """Throughput of the other fused launches of the path at 1 M points (tcgen05 modes): translator + LBS
+    (CompositeDeformer.forward), its forward-mode Jacobian variant, the SDF value+gradient launch and the colour
+    network.  ALGORITHMIC FLOP per point: SURVEY 8d (translator 1 746 944, colour net 1 871 872, SDF 3 933 184;
+    the forward-mode launches carry 4 rows per point)."""
+    import recmv_b200.model as M
+    from recmv_b200 import synth as sy
+    P = 1 << 20
+    g = sy.generator(21)
+    pts = ((torch.rand((P, 3), generator=g) - 0.5) * 1.2).to(dev)
+    unit = torch.nn.functional.normalize(torch.randn((P, 3), generator=g), dim=1).to(dev)
+    feats = (torch.randn((P, 256), generator=g) * 0.1).to(dev)
+    conds = (torch.randn((1, 128), generator=g) * 0.1).to(dev)
+    poses, trans = sy.poses_trans(1, seed=11)
+    poses, trans = poses.to(dev), trans.to(dev)
+    torch.manual_seed(3)
+    tr = M.MLPTranslator(128, 6).to(dev)
+    rn = M.RenderingNetwork_view_norm(256, d_in=9, d_out=3, dims=[512] * 4, mode="idr", weight_norm=True,
+                                      multires_v=4, multires_n=0).to(dev)
+    tr.mlp_mode = rn.mlp_mode = mode
+    deformer = M.CompositeDeformer([tr, ren.skinner])
+    ratio = {"sdfRatio": None, "deformerRatio": None, "renderRatio": None}
+    bi = torch.zeros((P,), dtype=torch.long, device=dev)
+    sdf_net = ren.sdf_net
+    sdf_net.mlp_mode = mode
+
+    def rate(fn, flop_per_point):
+        with torch.no_grad():
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 5
+        return {"points_per_s": P / (ms * 1e-3), "ms_per_1M_points": ms,
+                "algorithmic_tflops": flop_per_point * P / (ms * 1e-3) / 1e12}
+
+    return {
+        "deformer_fwd (MLPTranslator + LBS, one launch)": rate(
+            lambda: deformer(pts, [conds, [poses, trans]], bi, ratio=ratio, offset_type="body"), 1746944),
+        "deformer_fwd_jac (value + 3x3 Jacobian, forward mode)": rate(
+            lambda: deformer.value_and_jacobian(pts, [conds, [poses, trans]], bi, ratio=ratio, offset_type="body"), 4 * 1746944),
+        "sdf_value_and_grad (forward mode)": rate(lambda: sdf_net.value_and_grad(pts, None), 4 * FLOP_PER_SAMPLE),
+        "rendernet_fwd (colour MLP)": rate(lambda: rn(pts, unit, unit, feats, ratio), 1871872),
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,6 +319,11 @@ def main():
               "faces": int(f.shape[0]), "algorithmic_bytes": mc_bytes,
               "note": "count + scan + D2H of (V,F) + allocate + vertex + face passes, end to end per call"}
 
+    # ---- the other networks of the path on the same engine (reported next to the headline, not part of it) -----------
+    secondary = None
+    if rank == 0 and mode != 0:
+        secondary = secondary_rates(dev, ren, mode)
+
     if rank == 0:
         peaks, src = measured_peaks()
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
@@ -310,7 +365,7 @@ def main():
                            "hits": nhit},
                 "clocks": sampler.summary(), "gpu_launches": launches,
                 "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "roofline": roof, "cpu_baseline": cpu, "mc": mc}
+                "roofline": roof, "cpu_baseline": cpu, "mc": mc, "secondary": secondary}
         if mc is not None:
             hbm = float(peaks.get("hbm_gbs", 6650.0))
             mc["roofline"] = {"bound": "hbm", "achieved": mc["algorithmic_bytes"] / (mc["ms_per_call"] * 1e-3) / 1e9,

@@ -186,3 +186,37 @@ def test_full_render_surface_normals_colour():
         col_ref = rn(xc[idx], n_ref, dirs[idx], net.rendcond.detach(), {"renderRatio": None})
     assert (rgb[idx] - col_ref).abs().max() < 2e-3 and rgb[~hit].abs().max() == 0
     net.mlp_mode = None
+
+
+def test_empty_inputs_and_error_behaviour():
+    """Edge cases at the boundary: empty batches return empty tensors without a launch; CPU tensors raise
+    RuntimeError like the reference's CHECK_INPUT (M3x3Inv.cpp:4-6); an unknown mode is RECMV_E_UNSUPPORTED."""
+    from recmv_b200 import model as M
+    net = _net("geo")
+    e3 = torch.empty((0, 3), device=DEV)
+    tr = M.MLPTranslator(128, 6).to(DEV)
+    rn = M.RenderingNetwork_view_norm(256, d_in=9, d_out=3, dims=[512] * 4, mode="idr", weight_norm=True,
+                                      multires_v=4, multires_n=0).to(DEV)
+
+    def run_all():
+        with torch.no_grad():
+            assert net(e3, None).shape == (0, 1) and net.rendcond.shape == (0, 256)
+            v, g = net.value_and_grad(e3, None)
+            assert v.shape[0] == 0 and g.shape == (0, 3)
+            out = tr(e3, torch.zeros((2, 128), device=DEV), torch.empty((0,), dtype=torch.long, device=DEV),
+                     ratio={"deformerRatio": None}, offset_type="body")
+            assert out.shape == (0, 3) and tr.offset["body"].shape == (0, 3)
+            assert rn(e3, e3, e3, torch.empty((0, 256), device=DEV), {"renderRatio": None}).shape == (0, 3)
+        inv, ok = ops.minv3x3(torch.empty((0, 3, 3), device=DEV))
+        assert inv.shape == (0, 3, 3) and ok.shape == (0,)
+
+    run_all()                       # first pass packs the weights (launches)
+    n0 = ops.launch_count()
+    run_all()
+    assert ops.launch_count() == n0     # empty batches launch nothing
+    with pytest.raises(RuntimeError):
+        ops.sdf_mlp_forward(torch.zeros((4, 3)), net.packed_weights())        # CPU tensor
+    with pytest.raises(RuntimeError):
+        ops.minv3x3(torch.zeros((4, 3, 3)))
+    with pytest.raises(_lib.RecmvError, match="status -5"):
+        ops.sdf_mlp_forward(torch.zeros((4, 3), device=DEV), net.packed_weights(), None, 99)
