@@ -291,6 +291,12 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           }
         }
       }
+      // drain: the releases of the last `nslots` slot uses are asynchronous tcgen05.commit arrivals that no load
+      // waits for any more; collect them before this CTA may exit (same hazard as the final pe_free, see below)
+      for (int k = 0; k < nslots; ++k) {
+        mbar_wait(BAR(kBarEmpty + slot), ring ^ 1u, abort_flag, prm.status, 110 + slot);
+        if (++slot == nslots) { slot = 0; ring ^= 1u; }
+      }
     }
   } else if (warp == 1 || warp == 3) {
     // ====================== MMA issuers (leader CTA only): warp 1 -> N tile 0, warp 3 -> N tile 1 ===============
@@ -688,32 +694,46 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
       } else if (kNet == 1) {
         // deformer input row: [PE(p) (39) | cond[frame] (128) | 0 (25)] = three 64-wide K blocks written into the
         // activation buffer itself (free again once the previous tile's last layer has been issued and done)
-        float in[192];
+        // (written 8 columns at a time; only the 40-wide head [PE | first cond value] lives in registers)
+        float head[40];
 #pragma unroll
-        for (int e = 0; e < 192; ++e) in[e] = 0.f;
-        if (p < prm.P) {
+        for (int e = 0; e < 40; ++e) head[e] = 0.f;
+        const bool live = p < prm.P;
+        const bool value_row = !kJvp || (row & 3) == 0;
+        const float* cond = prm.conds;
+        if (live) {
           const float x = __ldg(prm.src.x + 3 * p), y = __ldg(prm.src.x + 3 * p + 1), z = __ldg(prm.src.x + 3 * p + 2);
-          if (!kJvp || (row & 3) == 0) {
-            positional_encode(x, y, z, prm.pw.w, in);
+          if (value_row) {
+            positional_encode(x, y, z, prm.pw.w, head);
             long long f = prm.batch_inds ? prm.batch_inds[p] : (prm.points_per_frame > 0 ? p / prm.points_per_frame : 0);
             f = f < 0 ? 0 : (f >= prm.num_frames ? prm.num_frames - 1 : f);
-            const float4* c = reinterpret_cast<const float4*>(prm.conds + (size_t)f * 128);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const float4 t = __ldg(c + e);
-              in[39 + 4 * e] = t.x; in[40 + 4 * e] = t.y; in[41 + 4 * e] = t.z; in[42 + 4 * e] = t.w;
-            }
+            cond = prm.conds + (size_t)f * 128;
+            head[39] = __ldg(cond);
           } else {
-            positional_encode_tangent(x, y, z, (row & 3) - 1, prm.pw.w, in);   // the condition does not depend on p
+            positional_encode_tangent(x, y, z, (row & 3) - 1, prm.pw.w, head);   // the condition does not depend on p
           }
 #pragma unroll
-          for (int e = 0; e < 167; ++e) in[e] *= kActScale;
+          for (int e = 0; e < 40; ++e) head[e] *= kActScale;
         }
         if (it > 0) mbar_wait(BAR(kBarPeFree), (uint32_t)((it - 1) & 1), abort_flag, prm.status, 400);
 #pragma unroll
-        for (int chunk = 0; chunk < 24; ++chunk) {
+        for (int chunk = 0; chunk < 5; ++chunk) {          // columns 0..39
           uint4 hi, lo;
-          split8(in + 8 * chunk, hi, lo);
+          split8(head + 8 * chunk, hi, lo);
+          const uint32_t off = sw128_offset(row, chunk);
+          st_shared_v4(base + kOffAHi + off, hi);
+          if (passes == 3) st_shared_v4(base + kOffALo + off, lo);
+        }
+#pragma unroll 1
+        for (int chunk = 5; chunk < 24; ++chunk) {         // columns 40..191: cond[1..127] then zeros
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int ci = 8 * chunk + e - 39;             // index into the condition vector
+            v[e] = (live && value_row && ci < 128) ? __ldg(cond + ci) * kActScale : 0.f;
+          }
+          uint4 hi, lo;
+          split8(v, hi, lo);
           const uint32_t off = (uint32_t)(chunk >> 3) * 8192u + sw128_offset(row, chunk & 7);
           st_shared_v4(base + kOffAHi + off, hi);
           if (passes == 3) st_shared_v4(base + kOffALo + off, lo);
@@ -751,6 +771,11 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(BAR(kBarPeReady), lrank);
     }
+    // The pe_free commit of the LAST tile is an asynchronous arrival (it fires when the tensor pipe retires the
+    // MMAs) that nobody consumes; for the deformer / colour networks it is issued after the final acc_full commit.
+    // Wait for it here so that it cannot land after this CTA has exited -- in the shared memory of the next
+    // launch's CTA (observed as a sporadic `unspecified launch failure` in back-to-back launches).
+    if (n_iter > 0) mbar_wait(BAR(kBarPeFree), (uint32_t)((n_iter - 1) & 1), abort_flag, prm.status, 401);
   }
 
   // ---- teardown: every role has drained; both CTAs must be done before TMEM goes away ---------------

@@ -190,7 +190,7 @@ def test_full_render_surface_normals_colour():
 
 def test_empty_inputs_and_error_behaviour():
     """Edge cases at the boundary: empty batches return empty tensors without a launch; CPU tensors raise
-    RuntimeError like the reference's CHECK_INPUT (M3x3Inv.cpp:4-6); an unknown mode is RECMV_E_UNSUPPORTED."""
+    RuntimeError like the reference's CHECK_INPUT (M3x3Inv.cpp:4-6); an unknown mode flag is RECMV_E_DTYPE."""
     from recmv_b200 import model as M
     net = _net("geo")
     e3 = torch.empty((0, 3), device=DEV)
@@ -218,5 +218,5 @@ def test_empty_inputs_and_error_behaviour():
         ops.sdf_mlp_forward(torch.zeros((4, 3)), net.packed_weights())        # CPU tensor
     with pytest.raises(RuntimeError):
         ops.minv3x3(torch.zeros((4, 3, 3)))
-    with pytest.raises(_lib.RecmvError, match="status -5"):
+    with pytest.raises(_lib.RecmvError, match="status -2"):   # RECMV_E_DTYPE: unknown dtype / layout / mode flag
         ops.sdf_mlp_forward(torch.zeros((4, 3), device=DEV), net.packed_weights(), None, 99)
