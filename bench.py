@@ -30,7 +30,7 @@ MODES = {"simt": 0, "tc3": 1, "tc1": 2}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE full-frame launch of the dominant kernel, from the
 # `ncu --set full` capture summarised in profiles/r01_ncu_summary.md (141.7 MB read + 52.0 MB written; the
 # algorithmic minimum is the 67 MB sdf output + the touched part of the 181 MB voxel + 8.6 MB of weights)
-TRAFFIC_BYTES = {"tc3": 294588416}   # 16 x (18 357 248 + 54 528) B: profiles/r01_ncu_tc3_current.txt (1/16 frame)
+TRAFFIC_BYTES = {"tc3": 193699072}
 
 
 def measured_peaks():
