@@ -185,6 +185,21 @@ RECMV_API int recmv_rendernet_fwd(const float* points, const float* normals, con
                         const float* feats, const void* packed, const float* pe_w /*host*/, float* out_rgb,
                         int64_t P, int mode, recmv_stream_t stream);
 
+/* ---- coarse-to-fine sweep helpers (A11, MCAcc/seg3d_lossless.py:233-428) -------------------------------------------
+ * interp2x_boundary3d: replaces MCAcc/cuda/interp2x_boundary3d.cpp:18-35 (forward(input, balance) -> [output,
+ * is_boundary]; backward(grad_output) -> grad_input).  input [NC,D,H,W] f32 -> output [NC,2D-1,2H-1,2W-1] f32 and
+ * is_boundary (1 byte per voxel: the contributing coarse voxels are not all on one side of balance_value).
+ * order 0 = the rounding of the reference extension (sequential sum / count), order 1 = the rounding of
+ * F.interpolate(mode='trilinear', align_corners=True), the reference's default path (seg3d_lossless.py:270-281).
+ * recmv_c2f_todo_mask: todo = (3x3x3 dilation of is_boundary) & ~done  (seg3d_lossless.py:297-303).                */
+RECMV_API int recmv_interp2x_boundary3d_fwd(const float* input, float* output, uint8_t* is_boundary, int NC,
+                                  int D, int H, int W, float balance_value, int order,
+                                  recmv_stream_t stream);
+RECMV_API int recmv_interp2x_boundary3d_bwd(const float* grad_output, float* grad_input, int NC, int D, int H,
+                                  int W, recmv_stream_t stream);
+RECMV_API int recmv_c2f_todo_mask(const uint8_t* is_boundary, const uint8_t* done, uint8_t* todo, int D, int H,
+                        int W, recmv_stream_t stream);
+
 /* Non-blocking health check of the tcgen05 path on the current device: every mbarrier wait in the kernel is
  * bounded; a wait that times out records {code, barrier tag, block} in mapped host memory and later launches
  * are refused with RECMV_E_DEVICE.  info may be NULL; clear != 0 resets the record.                        */

@@ -278,3 +278,53 @@ def surface_loss(sdf_val, defp, cam_pos, rays, w1=3.05, w2=1.0):
 
 def rad2deg_asin(s):
     return torch.arcsin(s) * 180.0 / math.pi
+
+
+# ----------------------------------------------------------------------------------------------
+# interp2x_boundary3d (MCAcc/cuda/interp2x_boundary3d_kernel.cu:9-129 forward, :131-242 backward)
+# ----------------------------------------------------------------------------------------------
+def interp2x_boundary3d(inp, balance_value):
+    """2x-1 upsampling of [N,C,D,H,W] with the reference kernel's per-parity-class formulas and summation order
+    (left to right), plus the 'neighbours not all on one side of balance_value' flag."""
+    N, C, D, H, W = inp.shape
+    out = inp.new_zeros((N, C, 2 * D - 1, 2 * H - 1, 2 * W - 1))
+    flag = torch.zeros(out.shape, dtype=torch.bool)
+
+    def sl(odd, n):      # (fine-index slice, [coarse slices of the contributing neighbours along this axis])
+        return (slice(1, None, 2), [slice(0, n - 1), slice(1, n)]) if odd else (slice(0, None, 2), [slice(0, n)])
+
+    for oz in (0, 1):
+        for oy in (0, 1):
+            for ox in (0, 1):
+                fz, cz = sl(oz, D)
+                fy, cy = sl(oy, H)
+                fx, cx = sl(ox, W)
+                # neighbour order of the reference kernel: x fastest then y then z, EXCEPT the two 4-neighbour classes
+                # with z odd, where z varies fastest (kernel lines 81-112)
+                if oz and (ox + oy == 1):
+                    order = [(a, b, c) for b in range(len(cy)) for c in range(len(cx)) for a in range(len(cz))]
+                else:
+                    order = [(a, b, c) for a in range(len(cz)) for b in range(len(cy)) for c in range(len(cx))]
+                vs = [inp[:, :, cz[a], cy[b], cx[c]] for a, b, c in order]
+                s = vs[0]
+                for v in vs[1:]:
+                    s = s + v
+                n = len(vs)
+                out[:, :, fz, fy, fx] = s if n == 1 else (s.double() / float(n)).to(inp.dtype)
+                fl = torch.stack([v > balance_value for v in vs])
+                flag[:, :, fz, fy, fx] = fl.any(0) & ~fl.all(0)
+    return out, flag
+
+
+def interp2x_boundary3d_backward(grad_out):
+    """Adjoint of the upsampling: weights 1, 1/2, 1/4, 1/8 by the number of odd offsets (kernel lines 154-238)."""
+    N, C, d, h, w = grad_out.shape
+    D, H, W = (d + 1) // 2, (h + 1) // 2, (w + 1) // 2
+    gp = torch.nn.functional.pad(grad_out, (1, 1, 1, 1, 1, 1))
+    gi = grad_out.new_zeros((N, C, D, H, W))
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                wgt = 0.5 ** (abs(dz) + abs(dy) + abs(dx))
+                gi = gi + wgt * gp[:, :, 1 + dz:1 + dz + d:2, 1 + dy:1 + dy + h:2, 1 + dx:1 + dx + w:2]
+    return gi

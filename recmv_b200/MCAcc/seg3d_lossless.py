@@ -52,8 +52,11 @@ class Seg3dLossless(nn.Module):
         self.balance_value = balance_value
         self.channels = channels
         assert channels == 1 and align_corners == False and visualize == False
-        assert not faster and not use_shadow and not use_cuda_impl, \
-            "only the default (_forward, torch upsampling) path of the reference is mirrored"
+        assert not faster and not use_shadow, "the _forward path of the reference is mirrored (faster / shadow are not)"
+        # use_cuda_impl=True: the reference's optional fused upsampler (its own rounding, seg3d_lossless.py:267-268).
+        # Default: the F.interpolate rounding -- evaluated by the same fused kernel on CUDA tensors (bit-identical to
+        # the two torch interpolations + compare, see csrc/c2f.cu), by torch ops on CPU tensors.
+        self.use_cuda_impl = use_cuda_impl
         self.align_corners = align_corners
         for r in resolutions:
             assert r[0] % 2 == 1 and r[1] % 2 == 1, f"resolution {r} need to be odd becuase of align_corner."
@@ -117,17 +120,33 @@ class Seg3dLossless(nn.Module):
                 calculated[::sz, ::sy, ::sx] = True
                 self.stats.append((W, H, D, D * H * W))
                 continue
-            with torch.no_grad():
-                valid = F.interpolate((occ > self.balance_value).float(), size=(D, H, W), mode="trilinear",
-                                      align_corners=True)
-            occ = F.interpolate(occ.float(), size=(D, H, W), mode="trilinear", align_corners=True)
-            with torch.no_grad():
+            fused = occ.is_cuda and not (torch.is_grad_enabled() and occ.requires_grad)
+            if fused:
+                from .. import ops
+                occ, boundary = ops.interp2x_boundary3d_forward(occ.float().contiguous(), self.balance_value,
+                                                                0 if self.use_cuda_impl else 1)
+                self.last_sweep_path = "fused"
+            elif self.use_cuda_impl:
+                from .interp2x_boundary3d import Interp2xBoundary3dFunction
+                occ, boundary = Interp2xBoundary3dFunction.apply(occ.float().contiguous(), self.balance_value)
+                self.last_sweep_path = "fused-autograd"
+            else:
+                with torch.no_grad():
+                    valid = F.interpolate((occ > self.balance_value).float(), size=(D, H, W), mode="trilinear",
+                                          align_corners=True)
+                occ = F.interpolate(occ.float(), size=(D, H, W), mode="trilinear", align_corners=True)
                 boundary = (valid > 0.0) & (valid < 1.0)
-                boundary = (F.conv3d(boundary.float(), self.smooth_w, padding=1) > 0)[0, 0]
+                self.last_sweep_path = "torch"
+            with torch.no_grad():
                 done_up = torch.zeros((D, H, W), dtype=torch.bool, device=dev)
                 done_up[::2, ::2, ::2] = done
                 done = done_up
-                todo = boundary & ~done
+                if occ.is_cuda:
+                    from .. import ops
+                    todo = ops.c2f_todo_mask(boundary[0, 0].contiguous(), done)
+                else:
+                    boundary = (F.conv3d(boundary.float(), self.smooth_w, padding=1) > 0)[0, 0]
+                    todo = boundary & ~done
             occ = occ.contiguous()
             queried = 0
             idx, interp, vals = self._query_mask(todo, stride, occ[0, 0], False, **kwargs)

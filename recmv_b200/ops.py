@@ -501,6 +501,49 @@ def render_sdf(ray_dirs, cam_pos, t_near, t_far, samples, A, trans, ws_cl, cente
     return sdf, xc, hit_idx, hit_t
 
 
+def interp2x_boundary3d_forward(inp, balance_value, order=0):
+    """[N,C,D,H,W] f32 -> (output [N,C,2D-1,2H-1,2W-1] f32, is_boundary bool): the reference's optional
+    `interp2x_boundary3d.forward` (order 0: its rounding; order 1: the rounding of F.interpolate(trilinear,
+    align_corners=True), the default path of Seg3dLossless)."""
+    _check_input(inp, "input")
+    if inp.dtype != torch.float32 or inp.dim() != 5:
+        raise RuntimeError("interp2x_boundary3d: expected a float32 [N,C,D,H,W] tensor")
+    N, C, D, H, W = inp.shape
+    out = torch.empty((N, C, 2 * D - 1, 2 * H - 1, 2 * W - 1), dtype=torch.float32, device=inp.device)
+    flag = torch.empty(out.shape, dtype=torch.uint8, device=inp.device)
+    with torch.cuda.device(inp.device):
+        check(_lib.load().recmv_interp2x_boundary3d_fwd(_ptr(inp), _ptr(out), _ptr(flag), N * C, D, H, W,
+                                                        float(balance_value), int(order), _stream(inp)),
+              "recmv_interp2x_boundary3d_fwd")
+    return [out, flag.view(torch.bool)]
+
+
+def interp2x_boundary3d_backward(grad_output):
+    """grad_output [N,C,2D-1,2H-1,2W-1] f32 -> grad_input [N,C,D,H,W] (`interp2x_boundary3d.backward`)."""
+    _check_input(grad_output, "grad_output")
+    if grad_output.dtype != torch.float32 or grad_output.dim() != 5:
+        raise RuntimeError("interp2x_boundary3d: expected a float32 [N,C,d,h,w] tensor")
+    N, C, d, h, w = grad_output.shape
+    D, H, W = (d + 1) // 2, (h + 1) // 2, (w + 1) // 2
+    gi = torch.empty((N, C, D, H, W), dtype=torch.float32, device=grad_output.device)
+    with torch.cuda.device(gi.device):
+        check(_lib.load().recmv_interp2x_boundary3d_bwd(_ptr(grad_output), _ptr(gi), N * C, D, H, W, _stream(gi)),
+              "recmv_interp2x_boundary3d_bwd")
+    return gi
+
+
+def c2f_todo_mask(is_boundary, done):
+    """(3x3x3 dilation of is_boundary [D,H,W] bool) & ~done [D,H,W] bool -> bool [D,H,W]."""
+    _check_input(is_boundary, "is_boundary")
+    _check_input(done, "done")
+    D, H, W = is_boundary.shape
+    todo = torch.empty((D, H, W), dtype=torch.uint8, device=done.device)
+    with torch.cuda.device(done.device):
+        check(_lib.load().recmv_c2f_todo_mask(_ptr(is_boundary.view(torch.uint8)), _ptr(done.view(torch.uint8)),
+                                              _ptr(todo), D, H, W, _stream(todo)), "recmv_c2f_todo_mask")
+    return todo.view(torch.bool)
+
+
 def check_async_errors(clear=False):
     """Raise if a tcgen05 launch on the current device aborted on a bounded wait (non-blocking check)."""
     info = (ctypes.c_int * 3)()

@@ -54,3 +54,23 @@ def test_bit_identical_to_reference_class():
     assert torch.equal(a, b)
     for name in ("spacing_x", "spacing_y", "spacing_z", "bx", "by", "bz"):
         assert getattr(ref, name) == getattr(ours, name)
+
+
+def test_interp2x_boundary_oracle_pins():
+    """The restated upsampler against an independent implementation: values == F.interpolate(trilinear,
+    align_corners=True) up to fp32 rounding, flags == 'interpolated 0/1 occupancy strictly between 0 and 1' (the
+    reference's default path, seg3d_lossless.py:270-281), backward == autograd of the interpolation."""
+    import torch.nn.functional as F
+    from oracle import oracle_torch as ot
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((1, 2, 5, 6, 7), generator=g)
+    out, flag = ot.interp2x_boundary3d(x, 0.1)
+    size = (9, 11, 13)
+    ref = F.interpolate(x, size=size, mode="trilinear", align_corners=True)
+    valid = F.interpolate((x > 0.1).float(), size=size, mode="trilinear", align_corners=True)
+    assert out.shape == ref.shape and (out - ref).abs().max() < 1e-6
+    assert torch.equal(flag, (valid > 0) & (valid < 1))
+    go = torch.randn(ref.shape, generator=g)
+    xr = x.clone().requires_grad_(True)
+    F.interpolate(xr, size=size, mode="trilinear", align_corners=True).backward(go)
+    assert (ot.interp2x_boundary3d_backward(go) - xr.grad).abs().max() < 1e-5

@@ -11,6 +11,7 @@ import torch
 from conftest import GOLDEN, load_golden, norm_err
 sys.path.insert(0, GOLDEN)
 import make_golden as mg  # noqa: E402  (scene builders shared with the generator)
+from oracle import oracle_torch as ot  # noqa: E402
 from recmv_b200 import _lib, ops, synth  # noqa: E402
 from recmv_b200 import model as M  # noqa: E402
 from recmv_b200 import utils as U  # noqa: E402
@@ -188,3 +189,55 @@ def test_fused_deformer_jacobian_matches_autograd():
                                         t["batch_inds"], RATIO, "test", "body")
     assert (nrm - t["normals"]).abs().max() < 2e-4
     ops.check_async_errors()
+
+
+def test_interp2x_boundary3d_and_fused_sweep_bookkeeping():
+    """A11 helpers: order 0 == the restated reference kernel (bit-exact), order 1 == F.interpolate on the values and
+    on the occupancy flags (bit-exact: the default sweep stays bit-identical), backward, the dilated todo mask, the
+    drop-in module under its reference name, and the whole sweep with / without the fused bookkeeping."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(4)
+    for shape in ((1, 1, 9, 10, 11), (2, 3, 5, 4, 6), (1, 1, 33, 33, 33)):
+        x = torch.randn(shape, generator=g)
+        o_ref, f_ref = ot.interp2x_boundary3d(x, 0.1)
+        xd = x.to(DEV)
+        o0, f0 = ops.interp2x_boundary3d_forward(xd, 0.1, 0)
+        assert torch.equal(o0.cpu(), o_ref) and torch.equal(f0.cpu(), f_ref)
+        size = tuple(2 * s - 1 for s in shape[2:])
+        o1, f1 = ops.interp2x_boundary3d_forward(xd, 0.1, 1)
+        t_val = F.interpolate(xd, size=size, mode="trilinear", align_corners=True)
+        t_valid = F.interpolate((xd > 0.1).float(), size=size, mode="trilinear", align_corners=True)
+        assert torch.equal(o1, t_val) and torch.equal(f1, (t_valid > 0) & (t_valid < 1))
+        go = torch.randn(o_ref.shape, generator=g)
+        gi = ops.interp2x_boundary3d_backward(go.to(DEV))
+        assert (gi.cpu() - ot.interp2x_boundary3d_backward(go)).abs().max() < 1e-5
+        if shape[:2] == (1, 1):
+            done = (torch.rand(o_ref.shape[2:], generator=g) < 0.3).to(DEV)
+            smooth = torch.ones(1, 1, 3, 3, 3, device=DEV) / 27.0
+            want = (F.conv3d(f1.float(), smooth, padding=1) > 0)[0, 0] & ~done
+            assert torch.equal(ops.c2f_todo_mask(f1[0, 0].contiguous(), done), want)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(__file__)), "recmv_b200", "compat"))
+    import interp2x_boundary3d as ext                      # the reference's module name
+    out, fl = ext.forward(xd, 0.1)
+    assert torch.equal(out, o0) and fl.dtype == torch.bool and ext.backward(go.to(DEV)).shape == xd.shape
+    # the sweep: fused bookkeeping (default on CUDA) vs torch ops on the same device, same query function
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_c2f_cpu import KW, sphere_query
+    eng = Seg3dLossless(sphere_query, **KW).to(DEV)
+    a = eng.forward()
+    assert eng.last_sweep_path == "fused"
+    real = ops.interp2x_boundary3d_forward
+
+    def torch_path(inp, balance, order):
+        size = tuple(2 * s - 1 for s in inp.shape[2:])
+        v = F.interpolate((inp > balance).float(), size=size, mode="trilinear", align_corners=True)
+        return [F.interpolate(inp, size=size, mode="trilinear", align_corners=True), (v > 0) & (v < 1)]
+    ops.interp2x_boundary3d_forward = torch_path
+    try:
+        b = eng.forward()
+    finally:
+        ops.interp2x_boundary3d_forward = real
+    assert torch.equal(a, b)
+    eng_c = Seg3dLossless(sphere_query, use_cuda_impl=True, **KW).to(DEV)   # the reference's optional path
+    c = eng_c.forward()
+    assert (c - a).abs().max() < 1e-5 and bool(((c > 0) == (a > 0)).all())
