@@ -238,6 +238,6 @@ def test_interp2x_boundary3d_and_fused_sweep_bookkeeping():
     finally:
         ops.interp2x_boundary3d_forward = real
     assert torch.equal(a, b)
-    eng_c = Seg3dLossless(sphere_query, use_cuda_impl=True, **KW).to(DEV)   # the reference's optional path
+    eng_c = Seg3dLossless(sphere_query, **{**KW, "use_cuda_impl": True}).to(DEV)   # the reference's optional path
     c = eng_c.forward()
     assert (c - a).abs().max() < 1e-5 and bool(((c > 0) == (a > 0)).all())
