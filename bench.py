@@ -301,7 +301,7 @@ def main():
 
     # ---- second half of the BASELINE metric: marching-cubes cells/s on a 257^3 grid (256^3 cells) -----------
     mc = None
-    if rank == 0:
+    if rank == 0 and world == 1:   # the MC half of the metric and the secondary launches: N=1 line only
         grid = synth.sphere_sdf_grid(257, num=8, seed=3, device=dev)
         for _ in range(3):
             v, f = ops.mc_gpu(grid, 2 / 256, 2 / 256, 2 / 256, -1.0, -1.0, -1.0, 0.0)
@@ -321,7 +321,7 @@ def main():
 
     # ---- the other networks of the path on the same engine (reported next to the headline, not part of it) -----------
     secondary = None
-    if rank == 0 and mode != 0:
+    if rank == 0 and world == 1 and mode != 0:
         secondary = secondary_rates(dev, ren, mode)
 
     if rank == 0:
@@ -339,7 +339,7 @@ def main():
                         "per product to meet the 1e-4 fp32 parity bar, so frac <= 1/3 by construction; "
                         "issued_frac = tensor-pipe work actually issued over the same peak"}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N=1 only
             threads = best_cpu_threads()
             rays = 4096
             step = cpu_port_rate(rays, threads)
