@@ -200,6 +200,16 @@ RECMV_API int recmv_interp2x_boundary3d_bwd(const float* grad_output, float* gra
 RECMV_API int recmv_c2f_todo_mask(const uint8_t* is_boundary, const uint8_t* done, uint8_t* todo, int D, int H,
                         int W, recmv_stream_t stream);
 
+/* ---- implicit-surface gradient, per-ray algebra (engineer/networks/OptimNetwork.py:788-851) -------
+ * b = [grad_f_p ; [v]x J] (4x3), r = grad_l_p (b^T b)^-1 b^T with FastMinv's |det| < 1e-4 rule (ok = 0, zeros).
+ * Outputs: sdf_coef [n] = -r[0] (the cotangent the reference feeds to autograd.grad(sdf(p), params, .)),
+ * def_vec [n,3] = r[1:4] (-[v]x) (the cotangent for autograd.grad(D(p), params, .)), optional ray_grad [n,3] =
+ * r[1:4] [d - c]x (needs d_minus_c [n,3]).  All inputs [n,3] except jac [n,3,3] (row i = gradient of D_i), fp32.   */
+RECMV_API int recmv_surface_grad_coeffs(const float* grad_l_p, const float* grad_f_p, const float* jac,
+                              const float* rays, const float* d_minus_c /*may be NULL*/, float* sdf_coef,
+                              float* def_vec, float* ray_grad /*may be NULL*/, uint8_t* ok, int64_t n,
+                              recmv_stream_t stream);
+
 /* Non-blocking health check of the tcgen05 path on the current device: every mbarrier wait in the kernel is
  * bounded; a wait that times out records {code, barrier tag, block} in mapped host memory and later launches
  * are refused with RECMV_E_DEVICE.  info may be NULL; clear != 0 resets the record.                        */

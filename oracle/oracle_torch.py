@@ -328,3 +328,29 @@ def interp2x_boundary3d_backward(grad_out):
                 wgt = 0.5 ** (abs(dz) + abs(dy) + abs(dx))
                 gi = gi + wgt * gp[:, :, 1 + dz:1 + dz + d:2, 1 + dy:1 + dy + h:2, 1 + dx:1 + dx + w:2]
     return gi
+
+
+# ----------------------------------------------------------------------------------------------
+# implicit-surface gradient, per-ray algebra (engineer/networks/OptimNetwork.py:788-851, 862-873)
+# ----------------------------------------------------------------------------------------------
+def cross_matrix(v):
+    """[v]x with [v]x @ x = v x x (OptimNetwork.py:789-804)."""
+    m = torch.zeros((v.shape[0], 3, 3), dtype=v.dtype)
+    m[:, 0, 1] = -v[:, 2]; m[:, 0, 2] = v[:, 1]
+    m[:, 1, 0] = v[:, 2]; m[:, 1, 2] = -v[:, 0]
+    m[:, 2, 0] = -v[:, 1]; m[:, 2, 1] = v[:, 0]
+    return m
+
+
+def surface_grad_coeffs(grad_l_p, grad_f_p, jac, rays, d_minus_c=None):
+    """b = [grad_f ; [v]x J], r = grad_l (b^T b)^-1 b^T with the FastMinv rule; returns (-r[:,0], r[:,1:4] (-[v]x),
+    r[:,1:4] [d-c]x or None, ok) exactly as the reference composes them."""
+    vx = cross_matrix(rays)
+    a1 = vx.matmul(jac)
+    b = torch.cat([grad_f_p.view(-1, 1, 3), a1], dim=1)
+    btb = b.permute(0, 2, 1).matmul(b)
+    inv, ok = minv3x3_fwd(btb.contiguous())
+    rhs = grad_l_p.view(-1, 1, 3).matmul(inv.matmul(b.permute(0, 2, 1)))      # [N,1,4]
+    temp = rhs[:, :, -3:].matmul(-vx).view(-1, 3)
+    rg = rhs[:, :, -3:].matmul(cross_matrix(d_minus_c)).view(-1, 3) if d_minus_c is not None else None
+    return -rhs[:, 0, 0], temp, rg, ok

@@ -544,6 +544,27 @@ def c2f_todo_mask(is_boundary, done):
     return todo.view(torch.bool)
 
 
+def surface_grad_coeffs(grad_l_p, grad_f_p, jac, rays, d_minus_c=None):
+    """Per-ray algebra of propagateTmpPsGrad (OptimNetwork.py:788-851) in one launch.
+    Returns (sdf_coef [n], def_vec [n,3], ray_grad [n,3] or None, ok [n] bool)."""
+    args = [t.contiguous().float() for t in (grad_l_p, grad_f_p, jac, rays)]
+    for t, name in zip(args, ("grad_l_p", "grad_f_p", "jac", "rays")):
+        _check_input(t, name)
+    n = args[0].shape[0]
+    if args[2].shape != (n, 3, 3) or any(a.shape != (n, 3) for a in (args[0], args[1], args[3])):
+        raise RuntimeError("surface_grad_coeffs: expected [n,3], [n,3], [n,3,3], [n,3]")
+    dev = args[0].device
+    dc = d_minus_c.contiguous().float() if d_minus_c is not None else None
+    coef = torch.empty((n,), dtype=torch.float32, device=dev)
+    vec = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    rg = torch.empty((n, 3), dtype=torch.float32, device=dev) if dc is not None else None
+    ok = torch.empty((n,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().recmv_surface_grad_coeffs(*[_ptr(a) for a in args], _ptr(dc), _ptr(coef), _ptr(vec), _ptr(rg),
+                                                    _ptr(ok), n, _stream(coef)), "recmv_surface_grad_coeffs")
+    return coef, vec, rg, ok.view(torch.bool)
+
+
 def check_async_errors(clear=False):
     """Raise if a tcgen05 launch on the current device aborted on a bounded wait (non-blocking check)."""
     info = (ctypes.c_int * 3)()

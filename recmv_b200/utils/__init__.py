@@ -76,3 +76,19 @@ def compute_deformed_normals(sdf, deformer, ps, defconds, batch_inds, ratio, pha
 def compute_netRender_color(net, ps, ds, ns, vs, features, framefeatures, ratio):
     """utils/utils.py:252-264 (the per-frame condition is ignored by the reference as well)."""
     return net(ps, ns, vs, features, ratio)
+
+
+def implicit_surface_grad_coeffs(sdf, deformer, ps, rays, grad_l_p, defconds, batch_inds, ratio, offset_type=None,
+                                 cam_pos=None):
+    """The part of `propagateTmpPsGrad` (engineer/networks/OptimNetwork.py:726-879) between the two network
+    evaluations, without autograd: grad f and J = dD/dp from the two forward-mode launches, then ONE kernel for the
+    per-ray algebra (b = [grad f ; [v]x J], r = dL/dp (b^T b)^-1 b^T, FastMinv singularity rule).
+    Returns (sdf_coef [N], def_vec [N,3], ray_grad [N,3] or None, ok [N], d [N,3]): the caller back-propagates
+    `sdf_coef` through `sdf(ps)` and `def_vec` through `deformer(ps)` exactly as the reference does (lines 836-858)."""
+    from .. import ops
+    with torch.no_grad():
+        f, gf = sdf.value_and_grad(ps.detach(), ratio.get('sdfRatio') if isinstance(ratio, dict) else ratio)
+        d, J = _value_and_jacobian(deformer, ps.detach(), defconds, batch_inds, ratio, offset_type, False)
+        dc = (d - cam_pos.view(1, 3)) if cam_pos is not None else None
+        coef, vec, rg, ok = ops.surface_grad_coeffs(grad_l_p, gf, J, rays, dc)
+    return coef, vec, rg, ok, d

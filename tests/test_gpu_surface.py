@@ -241,3 +241,52 @@ def test_interp2x_boundary3d_and_fused_sweep_bookkeeping():
     eng_c = Seg3dLossless(sphere_query, **{**KW, "use_cuda_impl": True}).to(DEV)   # the reference's optional path
     c = eng_c.forward()
     assert (c - a).abs().max() < 1e-5 and bool(((c > 0) == (a > 0)).all())
+
+
+def test_surface_grad_coeffs_kernel_and_fused_pipeline():
+    """the per-ray algebra of propagateTmpPsGrad in one kernel vs its torch restatement (oracle,
+    fp32 and fp64), incl. FastMinv's singular flag; then the whole autograd-free pipeline (two forward-mode launches +
+    the kernel) vs the reference procedure (autograd gradient of f, three autograd passes for J, torch algebra)."""
+    g = torch.Generator().manual_seed(9)
+    n = 4099
+    gl, gf, v, dc = (torch.randn((n, 3), generator=g) for _ in range(4))
+    v = v / v.norm(dim=1, keepdim=True)
+    J = torch.eye(3).expand(n, 3, 3) + 0.3 * torch.randn((n, 3, 3), generator=g)
+    J[:7] = 0.0                                   # singular systems: b^T b has rank 1 -> flag false, zeros
+    coef, vec, rg, ok = ops.surface_grad_coeffs(gl.to(DEV), gf.to(DEV), J.to(DEV), v.to(DEV), dc.to(DEV))
+    c_o, v_o, r_o, ok_o = ot.surface_grad_coeffs(gl, gf, J, v, dc)
+    c64, v64, r64, ok64 = ot.surface_grad_coeffs(gl.double(), gf.double(), J.double(), v.double(), dc.double())
+    assert not ok[:7].any() and float(coef[:7].abs().max()) == 0.0
+    agree = ok.cpu() == ok_o
+    assert agree.float().mean() > 0.999           # |det| within rounding of the 1e-4 threshold may flip
+    bm = torch.cat([gf.view(-1, 1, 3), ot.cross_matrix(v).matmul(J)], dim=1).double()
+    det = torch.linalg.det(bm.permute(0, 2, 1).matmul(bm))
+    sel = (ok.cpu() & ok_o & ok64 & (det.abs() > 5e-2))   # well-conditioned systems (fp32 loses its digits near the threshold)
+    assert sel.float().mean() > 0.6
+    for a, b in ((coef, c64), (vec, v64), (rg, r64)):
+        err = (a.cpu().double()[sel] - b[sel]).abs().max() / b[sel].abs().max()
+        assert err < 1e-3, err                     # conditioning of b^T b amplifies fp32 rounding; the fp32 oracle:
+    print("kernel vs fp32 restatement:", float((coef.cpu()[sel] - c_o[sel]).abs().max() / c_o[sel].abs().max()))
+    # whole pipeline on the scene of the surface goldens
+    gs = load_golden("surface.npz")
+    t = {k: torch.from_numpy(x).to(DEV) for k, x in gs.items()}
+    sdf, deformer = _scene()
+    defconds = [t["conds"], [t["poses"], t["trans"]]]
+    cam = torch.tensor(synth.CAM_POS, device=DEV)
+    glp = torch.randn((t["ps"].shape[0], 3), generator=g).to(DEV)
+    coef, vec, rg, ok, d = U.implicit_surface_grad_coeffs(sdf, deformer, t["ps"], t["rays"], glp, defconds,
+                                                          t["batch_inds"], RATIO, "body", cam)
+    p = t["ps"].clone().requires_grad_(True)
+    f = sdf(p, RATIO)
+    gfp = torch.autograd.grad(f, p, torch.ones_like(f))[0]
+    dd = deformer(p, defconds, t["batch_inds"], ratio=RATIO, offset_type="body")
+    Jr = U.compute_Jacobian(p, dd, False, False)
+    c_r, v_r, r_r, ok_r = ot.surface_grad_coeffs(glp.cpu(), gfp.cpu(), Jr.cpu(), t["rays"].cpu(), (dd.detach() - cam).cpu())
+    bm = torch.cat([gfp.cpu().view(-1, 1, 3), ot.cross_matrix(t["rays"].cpu()).matmul(Jr.cpu())], dim=1).double()
+    det = torch.linalg.det(bm.permute(0, 2, 1).matmul(bm))
+    sel = ok.cpu() & ok_r & (det.abs() > 5e-2)
+    print("pipeline: well-conditioned rays", float(sel.float().mean()))
+    assert sel.float().mean() > 0.5
+    for a, b in ((coef, c_r), (vec, v_r), (rg, r_r)):
+        assert (a.cpu()[sel] - b[sel]).abs().max() / b[sel].abs().max() < 2e-3
+    ops.check_async_errors()
