@@ -210,6 +210,12 @@ RECMV_API int recmv_surface_grad_coeffs(const float* grad_l_p, const float* grad
                               float* def_vec, float* ray_grad /*may be NULL*/, uint8_t* ok, int64_t n,
                               recmv_stream_t stream);
 
+/* Calibration knob of the tcgen05 modes.  The tensor core accumulates in fp32 with truncation: each of the K/16
+ * MMAs that adds into the full-size accumulator loses on average ~2^-24 of it, a systematic bias towards zero.  The
+ * epilogue therefore scales a layer's raw accumulators by (1 + gain_per_kblock * K/64); the default gain is
+ * 4 * 2^-24 (measured optimum against the reference's fp32 results, tools/calibrate_acc_gain.py; 0 disables).      */
+RECMV_API int recmv_tc_set_acc_gain(int mode, float gain_per_kblock);
+
 /* Non-blocking health check of the tcgen05 path on the current device: every mbarrier wait in the kernel is
  * bounded; a wait that times out records {code, barrier tag, block} in mapped host memory and later launches
  * are refused with RECMV_E_DEVICE.  info may be NULL; clear != 0 resets the record.                        */

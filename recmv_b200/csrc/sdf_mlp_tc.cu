@@ -73,6 +73,7 @@ struct TcParams {
   float* out_feat;
   long long P;
   int passes;
+  float acc_gain_kb;  // relative accumulator gain per 64-wide K block of a layer (4 accumulating MMAs)
   DevStatus* status;
   // diagnostics: raw accumulator (before bias) of layer dbg_layer for tile 0 -> dbg_out [128][512]
   int dbg_layer;
@@ -125,8 +126,7 @@ __device__ __forceinline__ int kb_order(int l, int i) {
 // range fix-ups of __expf/__logf (3 more FMUL + 2 predicates each).
 __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float softplus100_scaled(uint32_t acc_bits, float bias_u) {
-  constexpr float kU1 = kAccUnscale * kSoftplusLog2Scale;
+__device__ __forceinline__ float softplus100_scaled(uint32_t acc_bits, float bias_u, float kU1 /* acc unscale * 100 log2 e */) {
   constexpr float kUThr = 20.f * 1.4426950408889634f;
   constexpr float kC1 = 0.0069314718055994531f * kActScale;    // ln2 / 100
   constexpr float kC2 = kActScale / kSoftplusLog2Scale;
@@ -458,6 +458,10 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         const uint32_t use = (uint32_t)(L >> 1);
         const float* bias = prm.bias + l * 512;
         const bool hidden = l < kNumLayers - 1;
+        // 2^-16 x (1 + compensation of the tensor core's truncating accumulation: every one of the K/16 hi*hi
+        // MMAs that adds into the full-size fp32 accumulator drops on average ~2^-24 of it; recmv_tc_set_acc_gain)
+        const float acc_unscale = kAccUnscale * (1.f + prm.acc_gain_kb * (float)NetT::nkb(l));
+        const float acc_u1 = acc_unscale * kSoftplusLog2Scale;
         // hidden layers: 4 chunks of kCw columns per warp, chunk c = (N tile c >> 1, K block c & 1 of this half)
         const float* bsel = (!kJvp && kNet == 0) ? bias + kNumLayers * 512 : bias;   // SDF: the b * 100 log2 e plane
         auto f0_of = [&](int c) { return (c >> 1) * 256 + half * 128 + (c & 1) * 64 + grp * kCw; };
@@ -502,14 +506,14 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
               float v[8];
               if (!kJvp && kNet == 0) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = softplus100_scaled(r[8 * j + e], bcur[8 * j + e]);
+                for (int e = 0; e < 8; ++e) v[e] = softplus100_scaled(r[8 * j + e], bcur[8 * j + e], acc_u1);
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[8 * j + e]), kAccUnscale, bcur[8 * j + e]);
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(__uint_as_float(r[8 * j + e]), acc_unscale, bcur[8 * j + e]);
                 if (kJvp) {
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
-                    const float z_own = is_value ? v[e] : __uint_as_float(r[8 * j + e]) * kAccUnscale;  // tangents: no bias
+                    const float z_own = is_value ? v[e] : __uint_as_float(r[8 * j + e]) * acc_unscale;  // tangents: no bias
                     const float z_val = __shfl_sync(0xffffffffu, z_own, lane & ~3);  // the point's value row
                     v[e] = (kNet == 0 ? act_jvp(z_own, z_val, is_value) : (z_val > 0.f ? z_own : 0.f)) * kActScale;
                   }
@@ -556,7 +560,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
               if (p < prm.P && half == 0 && c0 == 0) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                  prm.out_rgb[3 * p + c] = tanhf(fmaf(__uint_as_float(r[c]), kAccUnscale, __ldg(bias + c)));
+                  prm.out_rgb[3 * p + c] = tanhf(fmaf(__uint_as_float(r[c]), acc_unscale, __ldg(bias + c)));
               }
             } else if (kNet == 1) {
               // deformer: columns 0..2 of the tail tile = offset; out = p + offset, then LBS forward
@@ -565,7 +569,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                   float dv[3], dt[9];         // offset and d offset_c / d p_j
 #pragma unroll
                   for (int c = 0; c < 3; ++c) {
-                    const float own = __uint_as_float(r[c]) * kAccUnscale;
+                    const float own = __uint_as_float(r[c]) * acc_unscale;
                     dv[c] = own + __ldg(bias + c);
 #pragma unroll
                     for (int j = 0; j < 3; ++j) dt[3 * c + j] = __shfl_sync(0xffffffffu, own, (lane & ~3) + 1 + j);
@@ -595,9 +599,9 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                   }
                 }
               } else if (p < prm.P && half == 0 && c0 == 0) {
-                const float dx = fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias + 0));
-                const float dy = fmaf(__uint_as_float(r[1]), kAccUnscale, __ldg(bias + 1));
-                const float dz = fmaf(__uint_as_float(r[2]), kAccUnscale, __ldg(bias + 2));
+                const float dx = fmaf(__uint_as_float(r[0]), acc_unscale, __ldg(bias + 0));
+                const float dy = fmaf(__uint_as_float(r[1]), acc_unscale, __ldg(bias + 1));
+                const float dz = fmaf(__uint_as_float(r[2]), acc_unscale, __ldg(bias + 2));
                 const float x = __ldg(prm.src.x + 3 * p), y = __ldg(prm.src.x + 3 * p + 1), z = __ldg(prm.src.x + 3 * p + 2);
                 const float tx = x + dx, ty = y + dy, tz = z + dz;
                 if (prm.out_translated) { prm.out_translated[3 * p] = tx; prm.out_translated[3 * p + 1] = ty; prm.out_translated[3 * p + 2] = tz; }
@@ -618,18 +622,18 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
               // last layer: column 0 = sdf, columns 1..256 = features
               const bool ok = valid[(it & 1) * 64 + row] != 0;
               if (kJvp && !is_value) {
-                if (!small && f0 == 0) prm.out_grad[p * 3 + (comp - 1)] = __uint_as_float(r[0]) * kAccUnscale;
+                if (!small && f0 == 0) prm.out_grad[p * 3 + (comp - 1)] = __uint_as_float(r[0]) * acc_unscale;
               } else if (!small) {
-                if (f0 == 0) prm.out_sdf[p] = ok ? fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias)) : kInvalidSdf;
+                if (f0 == 0) prm.out_sdf[p] = ok ? fmaf(__uint_as_float(r[0]), acc_unscale, __ldg(bias)) : kInvalidSdf;
                 if (prm.out_feat) {
 #pragma unroll
                   for (int c = 0; c < kCw; ++c) {
                     const int f = f0 + c;
-                    if (f > 0) prm.out_feat[p * 256 + (f - 1)] = fmaf(__uint_as_float(r[c]), kAccUnscale, __ldg(bias + f));
+                    if (f > 0) prm.out_feat[p * 256 + (f - 1)] = fmaf(__uint_as_float(r[c]), acc_unscale, __ldg(bias + f));
                   }
                 }
               } else if (half == 0 && c0 == 0 && prm.out_feat) {
-                prm.out_feat[p * 256 + 255] = fmaf(__uint_as_float(r[0]), kAccUnscale, __ldg(bias + 256));
+                prm.out_feat[p * 256 + 255] = fmaf(__uint_as_float(r[0]), acc_unscale, __ldg(bias + 256));
               }
             }
           }
@@ -788,6 +792,10 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
 
 namespace {
 DevStatus* g_status_host[16] = {nullptr};
+// relative compensation of the accumulation bias per 64-wide K block (= 4 accumulating hi*hi MMAs x 2^-24), per
+// precision mode {3 passes, 1 pass}; calibrated against the reference's fp32 results (tools/calibrate_acc_gain.py)
+float g_acc_gain_kb[2] = {4.f * 5.9604645e-8f, 4.f * 5.9604645e-8f};
+inline void set_acc_scales(TcParams& prm) { prm.acc_gain_kb = g_acc_gain_kb[prm.passes == 3 ? 0 : 1]; }
 
 // one mapped, pinned status record per device
 int tc_status_record(int dev, DevStatus** out) {
@@ -870,6 +878,7 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   prm.src = src; prm.pw = pw;
   prm.bias = (const float*)(pb + L.bias_all_off);
   prm.out_sdf = out_sdf; prm.out_feat = out_feat; prm.P = P; prm.passes = passes; prm.status = sd;
+  set_acc_scales(prm);
   prm.dbg_layer = dbg_layer; prm.dbg_out = dbg_out; prm.trace = trace; prm.out_grad = out_grad;
   const int pts_per_tile = out_grad ? 32 : 128;
   int64_t tiles = (P + pts_per_tile - 1) / pts_per_tile;
@@ -1022,6 +1031,7 @@ static int deformer_launch(const float* ps, const float* conds, const int64_t* b
   for (int i = 0; i < 12; ++i) prm.pw.w[i] = pe_w[i];
   prm.bias = (const float*)(pb + L.bias_off);
   prm.P = P; prm.passes = mode == RECMV_MLP_TC_F16X3 ? 3 : 1; prm.status = sd; prm.dbg_layer = -1;
+  set_acc_scales(prm);
   prm.conds = conds; prm.batch_inds = (const long long*)batch_inds; prm.points_per_frame = points_per_frame;
   prm.num_frames = num_frames; prm.bones = A; prm.trans = trans;
   if (vox) prm.vox = to_voxel(vox);
@@ -1109,6 +1119,7 @@ extern "C" int recmv_rendernet_fwd(const float* points, const float* normals, co
   for (int i = 0; i < 12; ++i) prm.pw.w[i] = i < 8 ? pe_w[i] : 0.f;
   prm.bias = (const float*)(pb + L.bias_off);
   prm.P = P; prm.passes = mode == RECMV_MLP_TC_F16X3 ? 3 : 1; prm.status = sd; prm.dbg_layer = -1;
+  set_acc_scales(prm);
   prm.normals = normals; prm.view_dirs = view_dirs; prm.feats = feats; prm.out_rgb = out_rgb;
   int64_t tiles = (P + 127) / 128;
   int64_t want = (tiles + kPairs - 1) / kPairs;
@@ -1116,6 +1127,15 @@ extern "C" int recmv_rendernet_fwd(const float* points, const float* normals, co
   int clusters = (int)(want < maxc ? want : maxc);
   sdf_tc_kernel<false, 2><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
   return launch_status();
+}
+
+// Diagnostics / calibration: relative gain per 64-wide K block applied to the raw accumulators of a precision mode
+// (RECMV_MLP_TC_F16X3 or RECMV_MLP_TC_F16X1) to compensate the tensor core's truncating accumulation.
+extern "C" int recmv_tc_set_acc_gain(int mode, float gain_per_kblock) {
+  if (mode != RECMV_MLP_TC_F16X3 && mode != RECMV_MLP_TC_F16X1) return RECMV_E_DTYPE;
+  if (!(fabsf(gain_per_kblock) < 1e-4f)) return RECMV_E_RANGE;
+  g_acc_gain_kb[mode == RECMV_MLP_TC_F16X3 ? 0 : 1] = gain_per_kblock;
+  return RECMV_OK;
 }
 
 // Reports (without synchronising) whether any tcgen05 launch on the current device has aborted on a bounded
