@@ -43,6 +43,10 @@ constexpr int kPairs = 1;  // MMA pairs per cluster sharing every weight tile th
                            // stream in lockstep and the frame gets SLOWER (tc3 1.41 -> 1.32 M rays/s, tc1 2.36 -> 2.08);
                            // clusters of 4 also only fit on 132 of the 148 SMs.
 constexpr int kRowsPerCta = 64;
+#ifndef RECMV_TC_TWO_SWEEPS
+#define RECMV_TC_TWO_SWEEPS 1   // last layer, parity mode: correction MMAs first, hi*hi MMAs in a second sweep
+#endif
+constexpr bool kTwoSweeps = RECMV_TC_TWO_SWEEPS != 0;
 constexpr int kSlots = 5;       // weight ring slots in their own region ...
 constexpr int kSlotsMax = 9;    // ... + 4 more in the (unused) activation lo plane when a single pass is issued
 constexpr uint32_t kSlotBytes = 16384;
@@ -272,7 +276,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           TRACE(3, it, l, 0);
           // last layer, parity mode: sweep 0 streams (w_hi, w_lo) for the correction MMAs, sweep 1 streams
           // w_hi again for the hi*hi MMAs (see the MMA issuer)
-          const int nsweep = (passes == 3 && l == kNumLayers - 1) ? 2 : 1;
+          const int nsweep = (kTwoSweeps && passes == 3 && l == kNumLayers - 1) ? 2 : 1;
           for (int sweep = 0; sweep < nsweep; ++sweep) {
             for (int i = 0; i < nkb; ++i) {
               const int kbi = NetT::kb_at(l, i);
@@ -354,7 +358,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           // hi*lo) are 2^-11 of the result: issued first, while the accumulator is still tiny, their
           // truncations are negligible; the 32 hi*hi MMAs follow in a second sweep over the K blocks
           // (96 -> 32 significant truncations).  Other layers keep one sweep (w_hi is streamed once).
-          const bool two_sweeps = (passes == 3 && l == kNumLayers - 1);
+          const bool two_sweeps = (kTwoSweeps && passes == 3 && l == kNumLayers - 1);
           for (int sweep = 0; sweep < (two_sweeps ? 2 : 1); ++sweep) {
             const int planes = (passes == 3 && sweep == 0) ? 2 : 1;   // slot uses per (K block, tile)
             for (int i = 0; i < nkb; ++i) {
