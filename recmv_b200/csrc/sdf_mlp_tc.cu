@@ -1,4 +1,4 @@
-// tcgen05 implementation of the fused SDF path.  ONE persistent kernel: for every tile of 128 points
+// tcgen05 implementation of the fused MLP paths.  ONE persistent kernel: for every tile of 128 points
 // (64 per CTA of a 2-CTA cluster) it runs  [ray -> x_obs -> skinning-voxel sample -> inverse LBS ->]
 // positional encoding -> 9 linears (+softplus) -> sdf / 256 features  with every activation kept
 // on-chip.  Replaces model/Embedder.py:43-50 + model/network.py:89-119 (and, in render mode, the
@@ -17,9 +17,14 @@
 //    rewritten IN PLACE by the epilogue (the full layer output sits in TMEM first), K-block by K-block,
 //    each K-block released to the MMA warp through its own mbarrier so the next layer starts as soon as
 //    its first 64 inputs exist.
-//  * warp roles: 0 TMA producer, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-11 epilogue (two warps per
-//    TMEM lane quadrant, one 64-column K block each: tcgen05.ld -> bias -> softplus -> hi/lo split ->
-//    swizzled st.shared), 12-13 prologue for the NEXT tile (point fetch / inverse LBS / PE).
+//  * warp roles (22 warps): 0 TMA producer; 1 and 3 MMA issuers of the leader CTA, one per N tile (independent
+//    accumulators; barrier polls issued one step ahead of use -- see the note at the issuer code); 2 TMEM
+//    allocator; 4-19 epilogue (four warps per TMEM lane quadrant, 16 columns per chunk: tcgen05.ld -> base-2
+//    softplus straight from the raw accumulator with the accumulation-bias compensation -> fp16 hi/lo split ->
+//    swizzled st.shared); 20-21 prologue for the NEXT tile (point fetch / inverse LBS / PE, or the input rows of
+//    the translator / colour networks).
+//  * the same engine runs three networks (Net<0> SDF, Net<1> translator + LBS, Net<2> colour) and a forward-mode
+//    (value + tangents, 4 rows per point) variant of the first two.
 // Every mbarrier wait is bounded: a protocol bug surfaces as a status code, not a hung GPU.
 #include "sdf_mlp.cuh"
 #include "tc_common.cuh"
