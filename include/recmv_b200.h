@@ -200,6 +200,21 @@ RECMV_API int recmv_interp2x_boundary3d_bwd(const float* grad_output, float* gra
 RECMV_API int recmv_c2f_todo_mask(const uint8_t* is_boundary, const uint8_t* done, uint8_t* todo, int D, int H,
                         int W, recmv_stream_t stream);
 
+/* ---- A10: surface-point solve of a batch of rays on the device (utils/FindSurfacePs.py:145-353) -------------------
+ * ps [P,3]: in = seeds (FindSurfacePs), out = solution; ok [P] = converged (|f| < dthreshold and the angle between
+ * D(p) - cam and the ray < athreshold_deg).  Networks: packed SDF weights, packed translator weights + conds
+ * [F,128] + skeleton (A [F,24,4,4], trans [F,3]) + channels-last voxel, i.e. the CompositeDeformer
+ * [MLPTranslator, LBSkinner]; batch_inds [P] i64 (or NULL: one frame).  `times` steps = times + 1 rounds of two
+ * forward-mode launches + one update kernel; no host synchronisation.  workspace: recmv_surface_solve_workspace(P)
+ * bytes of device memory.  TC modes only.                                                                            */
+RECMV_API size_t recmv_surface_solve_workspace(int64_t P);
+RECMV_API int recmv_surface_solve(const float* cam_pos /*host[3]*/, const float* rays, float* ps,
+                        const int64_t* batch_inds, const void* sdf_packed, const float* sdf_pe_w /*host[12]*/,
+                        const void* tr_packed, const float* tr_pe_w /*host[12]*/, const float* conds,
+                        int num_frames, const float* A, const float* trans, const recmv_voxel_t* vox /*host*/,
+                        float dthreshold, float athreshold_deg, float w1, float w2, int times, int mode,
+                        void* workspace, size_t workspace_bytes, uint8_t* ok, int64_t P, recmv_stream_t stream);
+
 /* ---- implicit-surface gradient, per-ray algebra (engineer/networks/OptimNetwork.py:788-851) -------
  * b = [grad_f_p ; [v]x J] (4x3), r = grad_l_p (b^T b)^-1 b^T with FastMinv's |det| < 1e-4 rule (ok = 0, zeros).
  * Outputs: sdf_coef [n] = -r[0] (the cotangent the reference feeds to autograd.grad(sdf(p), params, .)),

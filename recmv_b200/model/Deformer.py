@@ -64,6 +64,24 @@ class CompositeDeformer(nn.Module):
         graph; utils.compute_Jacobian semantics: row i = gradient of D_i).  None when this composite is not fusable."""
         return self._fused_forward(ps.detach(), conds, batch_inds, kwargs, want_jacobian=True)
 
+    def device_solve_args(self, conds, ratio):
+        """Everything `ops.surface_solve` needs from this deformer when it is the fusable [MLPTranslator, LBSkinner]
+        composite on CUDA: (translator packed weights, translator PE weights, conds [F,128], skin tuple, mode);
+        None otherwise."""
+        if self.N != 2 or not isinstance(self.defs[0], MLPTranslator) or not isinstance(self.defs[1], LBSkinner):
+            return None
+        tr, sk = self.defs[0], self.defs[1]
+        if not tr.fusable or tr.mlp_mode == ops.MLP_FP32_SIMT or not conds[0].is_cuda:
+            return None
+        poses, trans = conds[1]
+        with torch.no_grad():
+            A = sk.bone_matrices(poses)
+            t = trans + sk.extra_trans
+        center = sk.bbox_center.view(-1)[:3].tolist()
+        extend = float(sk.bbox_extend.view(-1)[0])
+        return (tr.packed_weights(), ratio_to_weights(tr.multires, ratio['deformerRatio']), conds[0],
+                (A, t, sk.ws_channels_last(), center, extend), tr.mlp_mode)
+
     def _fused_forward(self, ps, conds, batch_inds, kwargs, want_jacobian=False):
         """[MLPTranslator, LBSkinner] without an autograd graph -> ONE launch (translator MLP on tcgen05, then
         the skinning-voxel sample + bone blend in the same kernel's epilogue)."""

@@ -544,6 +544,34 @@ def c2f_todo_mask(is_boundary, done):
     return todo.view(torch.bool)
 
 
+def surface_solve(cam_pos, rays, seeds, batch_inds, sdf_packed, sdf_pe_w, tr_packed, tr_pe_w, conds, skin, dthreshold,
+                  athreshold, w1, w2, times, mode=None):
+    """Device-resident surface solve (recmv_surface_solve).  skin = (A, trans, ws_cl, center, extend).
+    Returns (points [P,3], ok [P] bool); `seeds` is not modified."""
+    mode = DEFAULT_MLP_MODE if mode is None else mode
+    ps = seeds.detach().contiguous().float().clone()
+    rays = rays.contiguous().float()
+    _check_input(ps, "seeds")
+    _check_input(rays, "rays")
+    P = ps.shape[0]
+    dev = ps.device
+    A, trans, ws_cl, center, extend = skin
+    A, trans, conds = A.contiguous().float(), trans.contiguous().float(), conds.contiguous().float()
+    bi = batch_inds.contiguous().long() if batch_inds is not None else None
+    lib = _lib.load()
+    wsz = lib.recmv_surface_solve_workspace(P)
+    work = torch.empty((max(wsz, 1),), dtype=torch.uint8, device=dev)
+    ok = torch.empty((P,), dtype=torch.uint8, device=dev)
+    cam = (c_float * 3)(*[float(v) for v in cam_pos.view(-1).tolist()])
+    with torch.cuda.device(dev):
+        check(lib.recmv_surface_solve(cam, _ptr(rays), _ptr(ps), _ptr(bi), _ptr(sdf_packed), _pe_array(sdf_pe_w),
+                                      _ptr(tr_packed), _pe_array(tr_pe_w), _ptr(conds), int(conds.shape[0]), _ptr(A),
+                                      _ptr(trans), byref(make_voxel(ws_cl, center, extend)), float(dthreshold),
+                                      float(athreshold), float(w1), float(w2), int(times), mode, _ptr(work), wsz,
+                                      _ptr(ok), P, _stream(ps)), "recmv_surface_solve")
+    return ps, ok.view(torch.bool)
+
+
 def surface_grad_coeffs(grad_l_p, grad_f_p, jac, rays, d_minus_c=None):
     """Per-ray algebra of propagateTmpPsGrad (OptimNetwork.py:788-851) in one launch.
     Returns (sdf_coef [n], def_vec [n,3], ray_grad [n,3] or None, ok [n] bool)."""

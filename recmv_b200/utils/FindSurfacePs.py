@@ -34,6 +34,12 @@ def FindSurfacePs(TmpVs, TmpFaces, frags):
     return batch_inds, row_inds, col_inds, initTmpPs, finds
 
 
+# The three Optimize* entry points run the whole loop on the device (one C call) when both networks are on the
+# tcgen05 engine; set False to force the step-by-step torch loop (`_solve`, which also serves CPU tensors, the
+# fp32 SIMT mode and deformers other than [MLPTranslator, LBSkinner]).
+DEVICE_SOLVE = True
+
+
 def _angle_ok(direct, rays, athreshold):
     up = torch.cross(direct, rays, dim=1)
     return torch.arcsin(up.norm(dim=1) / direct.norm(dim=1)) * 180. / np.pi < athreshold
@@ -89,6 +95,28 @@ def _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthresho
     return initTmpPs.detach(), ~unfinished
 
 
+def _solve_device(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deformer, defconds, dthreshold, athreshold,
+                  w1, w2, times):
+    """The whole active-set loop as ONE C call (recmv_surface_solve: times + 1 rounds of two forward-mode launches +
+    an update kernel, no host synchronisation) when both networks run on the tcgen05 engine; None otherwise."""
+    from .. import ops
+    if not (initTmpPs.is_cuda and getattr(tmpSdf, "_fusable", False) and hasattr(deformer, "device_solve_args")):
+        return None
+    if tmpSdf.mlp_mode == ops.MLP_FP32_SIMT:
+        return None
+    args = deformer.device_solve_args(defconds, ratio)
+    if args is None or (args[4] or ops.DEFAULT_MLP_MODE) != (tmpSdf.mlp_mode or ops.DEFAULT_MLP_MODE):
+        return None
+    tr_packed, tr_pe, conds, skin, mode = args
+    sdf_ratio = ratio.get('sdfRatio') if isinstance(ratio, dict) else ratio
+    with torch.no_grad():
+        ps, ok = ops.surface_solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf.packed_weights(),
+                                   tmpSdf._pe_weights(sdf_ratio), tr_packed, tr_pe, conds, skin, dthreshold,
+                                   athreshold, w1, w2, times, mode)
+        initTmpPs.copy_(ps)            # the reference mutates and returns its seed tensor
+    return initTmpPs.detach(), ok
+
+
 def _jac_fn(deformer, conds_fn, ratio, offset_type):
     """(ps, inds) -> (D(ps), dD/dps) through the deformer's fused forward-mode launch, or None if it has none."""
     fn = getattr(deformer, "value_and_jacobian", None)
@@ -105,6 +133,11 @@ def _jac_fn(deformer, conds_fn, ratio, offset_type):
 
 def OptimizeSurfacePs(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deformer, defconds,
                       dthreshold=5.e-5, athreshold=0.02, w1=3.05, w2=1., times=5):
+    dev_res = _solve_device(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deformer, defconds, dthreshold,
+                            athreshold, w1, w2, times) if DEVICE_SOLVE else None
+    if dev_res is not None:
+        return dev_res
+
     def deform(ps, inds):
         return deformer(ps, defconds, inds, ratio=ratio)
     return _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2, times,
@@ -113,6 +146,11 @@ def OptimizeSurfacePs(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, defor
 
 def OptimizeGarmentSurfaceSinlge(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deformer, defconds,
                                  dthreshold=5.e-5, athreshold=0.02, w1=3.05, w2=1., times=5, offset_type=None):
+    dev_res = _solve_device(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deformer, defconds, dthreshold,
+                            athreshold, w1, w2, times) if DEVICE_SOLVE else None
+    if dev_res is not None:
+        return dev_res
+
     def deform(ps, inds):
         return deformer(ps, defconds, inds, ratio=ratio, offset_type=offset_type)
     return _solve(cam_pos, rays, initTmpPs, batch_inds, tmpSdf, ratio, deform, dthreshold, athreshold, w1, w2, times,
@@ -126,6 +164,13 @@ def OptimizeGarmentSurfacePs(cam_pos, rays_list, initTmpPs_list, batch_inds_list
     out_ps, out_ok = [], []
     for gi, (ps, inds, dcond, rays, name) in enumerate(zip(initTmpPs_list, batch_inds_list, defconds_list[0],
                                                             rays_list, garment_names)):
+        dev_res = _solve_device(cam_pos, rays, ps, inds, tmpSdf_nets[gi], ratio, deformer, [dcond, smpl_conds],
+                                dthreshold, athreshold, w1, w2, times) if DEVICE_SOLVE else None
+        if dev_res is not None:
+            out_ps.append(dev_res[0])
+            out_ok.append(dev_res[1])
+            continue
+
         def deform(p, i, dcond=dcond, name=name):
             return deformer(p, [dcond, smpl_conds], i, ratio=ratio, offset_type=name)
         p, ok = _solve(cam_pos, rays, ps, inds, tmpSdf_nets[gi], ratio, deform, dthreshold, athreshold, w1, w2, times,

@@ -290,3 +290,61 @@ def test_surface_grad_coeffs_kernel_and_fused_pipeline():
     for a, b in ((coef, c_r), (vec, v_r), (rg, r_r)):
         assert (a.cpu()[sel] - b[sel]).abs().max() / b[sel].abs().max() < 2e-3
     ops.check_async_errors()
+
+
+def test_device_surface_solve_matches_reference_and_torch_loop():
+    """A10 as ONE C call (recmv_surface_solve): against the reference's golden run (same bounds as the tc3 torch
+    loop: a point may pass the acceptance test one step earlier or later), against the step-by-step loop on the same
+    device, the single-step case, a single-frame call without batch indices, and timing of both."""
+    import time
+    from recmv_b200.utils import FindSurfacePs as FSP
+    g = load_golden("surface.npz")
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in g.items()}
+    sdf, deformer = _scene()
+    defconds = [t["conds"], [t["poses"], t["trans"]]]
+    cam = torch.tensor(synth.CAM_POS, device=DEV)
+    kw = dict(dthreshold=1.e-4, athreshold=0.05, w1=3.05, w2=1., times=10, offset_type="body")
+
+    def run(device_solve):
+        FSP.DEVICE_SOLVE = device_solve
+        try:
+            n0 = ops.launch_count()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ps, ok = U.OptimizeGarmentSurfaceSinlge(cam, t["rays"], t["seeds"].clone(), t["batch_inds"], sdf, RATIO,
+                                                    deformer, defconds, **kw)
+            torch.cuda.synchronize()
+            return ps, ok, (time.perf_counter() - t0) * 1e3, ops.launch_count() - n0
+        finally:
+            FSP.DEVICE_SOLVE = True
+    run(True); run(False)                                   # warm-up (weight packing, allocator)
+    ps_d, ok_d, ms_d, n_d = run(True)
+    ps_t, ok_t, ms_t, n_t = run(False)
+    print(f"device solve: {ms_d:.2f} ms, {n_d} launches | torch loop: {ms_t:.2f} ms, {n_t} launches | "
+          f"converged {int(ok_d.sum())} / {int(ok_t.sum())} / reference {int(t['ok'].sum())}")
+    assert n_d == 3 * 11                                    # (2 forward-mode launches + update) x (times + 1) rounds
+    for ps, ok in ((ps_d, ok_d),):
+        agree = (ok == t["ok"]).float().mean().item()
+        both = ok & t["ok"]
+        assert agree >= 0.97 and (ps - t["ps"])[both].abs().max() < 2.1e-3
+    both = ok_d & ok_t
+    assert (ok_d == ok_t).float().mean() >= 0.97 and (ps_d - ps_t)[both].abs().max() < 2.1e-3
+    # converged points satisfy the acceptance test when re-evaluated
+    with torch.no_grad():
+        f = sdf(ps_d[ok_d], RATIO).view(-1)
+        dd = deformer(ps_d[ok_d], defconds, t["batch_inds"][ok_d], ratio=RATIO, offset_type="body") - cam
+    up = torch.cross(dd, t["rays"][ok_d], dim=1)
+    ang = torch.arcsin(up.norm(dim=1) / dd.norm(dim=1)) * 180. / np.pi
+    assert f.abs().max() < 1.2e-4 and ang.max() < 0.051
+    # one step
+    sdf2, def2 = sdf, deformer
+    ps1, ok1 = U.OptimizeGarmentSurfaceSinlge(cam, t["rays"], t["seeds"].clone(), t["batch_inds"], sdf2, RATIO, def2,
+                                              defconds, dthreshold=1.e-4, athreshold=0.05, times=1, offset_type="body")
+    assert (ok1 == t["ok_1it"]).float().mean() >= 0.97 and (ps1 - t["ps_1it"]).abs().max() < 1e-3
+    # one frame, no batch indices
+    m = t["batch_inds"] == 0
+    ps0, ok0 = ops.surface_solve(cam, t["rays"][m], t["seeds"][m], None, sdf.packed_weights(), sdf._pe_weights(RATIO),
+                                 *deformer.device_solve_args([t["conds"][:1], [t["poses"][:1], t["trans"][:1]]], RATIO)[:4],
+                                 1.e-4, 0.05, 3.05, 1., 10)
+    assert (ok0 == ok_d[m]).float().mean() >= 0.97
+    ops.check_async_errors()
