@@ -297,7 +297,8 @@ def test_device_surface_solve_matches_reference_and_torch_loop():
     loop: a point may pass the acceptance test one step earlier or later), against the step-by-step loop on the same
     device, the single-step case, a single-frame call without batch indices, and timing of both."""
     import time
-    from recmv_b200.utils import FindSurfacePs as FSP
+    import importlib
+    FSP = importlib.import_module("recmv_b200.utils.FindSurfacePs")   # the module (utils re-exports a function of that name)
     g = load_golden("surface.npz")
     t = {k: torch.from_numpy(v).to(DEV) for k, v in g.items()}
     sdf, deformer = _scene()
@@ -322,7 +323,7 @@ def test_device_surface_solve_matches_reference_and_torch_loop():
     ps_t, ok_t, ms_t, n_t = run(False)
     print(f"device solve: {ms_d:.2f} ms, {n_d} launches | torch loop: {ms_t:.2f} ms, {n_t} launches | "
           f"converged {int(ok_d.sum())} / {int(ok_t.sum())} / reference {int(t['ok'].sum())}")
-    assert n_d == 3 * 11                                    # (2 forward-mode launches + update) x (times + 1) rounds
+    assert n_d == 3 * 11 and n_t != n_d                     # (2 forward-mode launches + update) x (times + 1) rounds
     for ps, ok in ((ps_d, ok_d),):
         agree = (ok == t["ok"]).float().mean().item()
         both = ok & t["ok"]
