@@ -34,7 +34,13 @@ def main():
     ref = open(os.path.join(REF, "MCGpu/CudaKernels.cu")).read()
     mine = open(os.path.join(HERE, "../recmv_b200/csrc/mc_tables.h")).read()
     ref_tri = ints(block(ref, "a2iTriangleConnectionTable[256][16]"))
-    my_tri = ints(block(mine, "kMcTriTable[256][16]"))
+    # our header keeps the table in compact form: one hex digit (edge id) per triangle corner, one string per case
+    strs = re.findall(r'"([0-9a-b]*)"', block(mine, "kMcTriHex[256]"))
+    assert len(strs) == 256, len(strs)
+    my_tri = []
+    for h in strs:
+        row = [int(ch, 16) for ch in h]
+        my_tri += row + [-1] * (16 - len(row))
     assert len(ref_tri) == len(my_tri) == 4096, (len(ref_tri), len(my_tri))
     bad = [i // 16 for i in range(4096) if ref_tri[i] != my_tri[i]]
     assert not bad, f"tri table differs in cases {sorted(set(bad))}"

@@ -50,13 +50,13 @@ int mc_oracle(const float* sdf, int NX, int NY, int NZ, float iso, const float s
       val[c] = sdf[id];
       if (val[c] < iso) flag |= 1 << c;
     }
-    if (kMcTriTable[flag][0] < 0) continue;
+    if (mc_tri_entry(flag, 0) < 0) continue;
     int is_new[12];
     for (int e = 0; e < 12; ++e) is_new[e] = 1;
-    for (int t = 0; t < 5 && kMcTriTable[flag][3 * t] >= 0; ++t) {
+    for (int t = 0; t < 5 && mc_tri_entry(flag, 3 * t) >= 0; ++t) {
       long long fid = nf++;
       for (int c = 0; c < 3; ++c) {
-        int e = kMcTriTable[flag][3 * t + c];
+        int e = mc_tri_entry(flag, 3 * t + c);
         int bx = i + kMcEdgeOwner[e][0], by = j + kMcEdgeOwner[e][1], bz = k + kMcEdgeOwner[e][2];
         int dir = kMcEdgeOwner[e][3];
         if (is_new[e] && (e == 0 || e == 3 || e == 8)) {

@@ -54,16 +54,16 @@ __device__ signed char g_mc_tri[256][16];
 static void build_tables(McTables& t) {
   for (int c = 0; c < 256; ++c) {
     int n = 0;
-    while (n < 5 && kMcTriTable[c][3 * n] >= 0) ++n;
+    while (n < 5 && mc_tri_entry(c, 3 * n) >= 0) ++n;
     t.ntri[c] = (unsigned char)n;
     int rank[3] = {3, 3, 3}, cnt = 0;
     for (int q = 0; q < 3 * n; ++q) {
-      int e = kMcTriTable[c][q];
+      int e = mc_tri_entry(c, q);
       int slot = e == 0 ? 0 : (e == 3 ? 1 : (e == 8 ? 2 : -1));
       if (slot >= 0 && rank[slot] == 3) rank[slot] = cnt++;
     }
     t.vinfo[c] = (unsigned char)(rank[0] | (rank[1] << 2) | (rank[2] << 4) | (cnt << 6));
-    for (int q = 0; q < 16; ++q) t.tri[c][q] = kMcTriTable[c][q];
+    for (int q = 0; q < 16; ++q) t.tri[c][q] = (signed char)mc_tri_entry(c, q);
   }
   for (int e = 0; e < 12; ++e)
     for (int q = 0; q < 4; ++q) t.owner[e][q] = kMcEdgeOwner[e][q];
