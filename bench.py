@@ -74,24 +74,36 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+_CPU_SCENE = {}
+
+
+def _cpu_scene():
+    """Weights, skinning voxel and skeleton of the CPU legs (built once per process)."""
+    if not _CPU_SCENE:
+        from oracle import oracle_torch as ot
+        from recmv_b200 import synth
+        from recmv_b200.model import LBSkinner, getTmpSdf
+        torch.manual_seed(0)
+        net = getTmpSdf("cpu", 6, 0.6, 256)
+        Ws, bs = net.effective_weights()
+        Js, parents, init = synth.skeleton()
+        ws = synth.skinning_voxel((65, 225, 129), seed=7)
+        sk = LBSkinner(ws, [-1.1] * 3, [1.1] * 3, Js, parents, init_pose=init,
+                       bbox_extend=torch.tensor(synth.BBOX_EXTEND), bbox_center=torch.tensor(synth.BBOX_CENTER))
+        poses, trans = synth.poses_trans(1, seed=11)
+        _CPU_SCENE.update(Ws=[w.detach() for w in Ws], bs=[b.detach() for b in bs], ws=ws, trans=trans,
+                          A=ot.bone_matrices(poses, Js, parents, sk.init_pose))
+    return _CPU_SCENE
+
+
 def cpu_port_rate(samples_rays, threads):
     """The oracle's CPU restatement of the same path (inverse LBS + SDF MLP), timed on the host cores.
     Bounded sample of the workload: `samples_rays` rays x 64 samples of frame 0."""
     from oracle import oracle_torch as ot
     from recmv_b200 import synth
-    from recmv_b200.model import getTmpSdf
     torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    net = getTmpSdf("cpu", 6, 0.6, 256)
-    Ws, bs = net.effective_weights()
-    Ws, bs = [w.detach() for w in Ws], [b.detach() for b in bs]
-    Js, parents, init = synth.skeleton()
-    from recmv_b200.model import LBSkinner
-    ws = synth.skinning_voxel((65, 225, 129), seed=7)
-    sk = LBSkinner(ws, [-1.1] * 3, [1.1] * 3, Js, parents, init_pose=init,
-                   bbox_extend=torch.tensor(synth.BBOX_EXTEND), bbox_center=torch.tensor(synth.BBOX_CENTER))
-    poses, trans = synth.poses_trans(1, seed=11)
-    A = ot.bone_matrices(poses, Js, parents, sk.init_pose)
+    sc = _cpu_scene()
+    Ws, bs, ws, trans, A = sc["Ws"], sc["bs"], sc["ws"], sc["trans"], sc["A"]
     dirs = synth.pinhole_rays(H, W)[H * W // 2: H * W // 2 + samples_rays]
     cam = torch.tensor(synth.CAM_POS)
     dt = (synth.T_FAR - synth.T_NEAR) / S
@@ -114,6 +126,8 @@ def best_cpu_threads():
     """torch-CPU throughput of the port peaks well below the core count of the GPU host (measured on the
     128-thread B200 host: 8 thr 1201, 16 thr 1443, 32 thr 1405, 64 thr 1022, 128 thr 37 rays/s --
     profiles/r01_notes.md): calibrate on a small sample and use the fastest setting."""
+    if os.environ.get("RECMV_BENCH_CPU_THREADS"):     # skip the calibration (tests)
+        return max(1, int(os.environ["RECMV_BENCH_CPU_THREADS"]))
     n = os.cpu_count() or 1
     best, best_rate = 1, 0.0
     for th in (8, 16, 32, 64, n):
@@ -137,7 +151,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = best_cpu_threads()
-    rays = 4096
+    rays = int(os.environ.get("RECMV_BENCH_REF_RAYS", "4096"))
     step = cpu_port_rate(rays, threads)
     for _ in range(min(args.warmup, 1)):
         step()
