@@ -236,7 +236,7 @@ RECMV_API int recmv_tc_set_acc_gain(int mode, float gain_per_kblock);
  * are refused with RECMV_E_DEVICE.  info may be NULL; clear != 0 resets the record.                        */
 RECMV_API int recmv_check_async_errors(int* info /*host [3]*/, int clear);
 
-/* Diagnostics for the tcgen05 path (used by tests/test_gpu_tc_bringup.py): same computation as
+/* Diagnostics for the tcgen05 path (used by tools/tc_bringup.py and tools/tc_trace.py): same computation as
  * recmv_sdf_mlp_fwd in a TC mode (passes = 1 or 3), plus status_host[4] = {code, barrier tag, block, 0}
  * of the kernel's bounded mbarrier waits (code 0 = no wait timed out) and, when dbg_out != NULL, the raw
  * fp32 accumulator (before bias) of layer dbg_layer for the first 128 points, [128][512].              */
