@@ -28,9 +28,9 @@ FLOP_PER_SAMPLE = 2 * 1966592  # 3 933 184 FLOP per SDF forward
 METRIC = "rays/sec at 512x512x64-samp SDF render"
 MODES = {"simt": 0, "tc3": 1, "tc1": 2}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE full-frame launch of the dominant kernel, from the
-# `ncu --set full` capture summarised in profiles/r01_ncu_summary.md (141.7 MB read + 52.0 MB written; the
+# ncu capture of the final round-1 kernel, profiles/r01_ncu_tc3_current.txt (142.3 MB read + 54.8 MB written; the
 # algorithmic minimum is the 67 MB sdf output + the touched part of the 181 MB voxel + 8.6 MB of weights)
-TRAFFIC_BYTES = {"tc3": 193699072}
+TRAFFIC_BYTES = {"tc3": 197053696}
 
 
 def measured_peaks():
