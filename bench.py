@@ -42,36 +42,64 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML in-process
+    every 20 ms (>= 20 samples even for a 0.5 s region); `nvidia-smi` as the fallback when NVML is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, cuda_index):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.gpu, self.rows, self.stop_flag, self.h, self.nv = cuda_index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _nvml_row(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        bits = (nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap)
+        return [str(self.gpu), str(sm), str(self.sm_max), str(pw)] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.h is not None:
+                    self.rows.append(self._nvml_row())
+                    time.sleep(0.02)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
                 for line in out.strip().splitlines():
                     self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        num = lambda v: v.replace(".", "", 1).isdigit()  # noqa: E731
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and num(r[1]))
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and num(r[2])]
+        pw = [float(r[3]) for r in self.rows if len(r) > 3 and num(r[3])]
         reasons = set()
         for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+            for name, v in zip(self.NAMES, r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "power_w_max": max(pw) if pw else None,
+                "source": "nvml" if self.h is not None else "nvidia-smi"}
 
 
 _CPU_SCENE = {}
@@ -125,19 +153,21 @@ def cpu_port_rate(samples_rays, threads):
 def best_cpu_threads():
     """torch-CPU throughput of the port peaks well below the core count of the GPU host (measured on the
     128-thread B200 host: 8 thr 1201, 16 thr 1443, 32 thr 1405, 64 thr 1022, 128 thr 37 rays/s --
-    profiles/r01_notes.md): calibrate on a small sample and use the fastest setting."""
+    profiles/r01_notes.md): calibrate on a small sample and use the fastest setting.  Bounded: candidates are
+    8/16/32/64 (never more threads than cores), each probe is 2 x 128 rays and the loop stops after 20 s."""
     if os.environ.get("RECMV_BENCH_CPU_THREADS"):     # skip the calibration (tests)
         return max(1, int(os.environ["RECMV_BENCH_CPU_THREADS"]))
     n = os.cpu_count() or 1
-    best, best_rate = 1, 0.0
-    for th in (8, 16, 32, 64, n):
-        if th > n:
+    best, best_rate = min(n, 8), 0.0
+    t_start = time.perf_counter()
+    for th in (16, 8, 32, 64):
+        if th > n or time.perf_counter() - t_start > 20.0:
             continue
-        step = cpu_port_rate(256, th)
+        step = cpu_port_rate(128, th)
         step()
         t0 = time.perf_counter()
         step()
-        rate = 256 / (time.perf_counter() - t0)
+        rate = 128 / (time.perf_counter() - t0)
         if rate > best_rate:
             best, best_rate = th, rate
     return best
@@ -167,7 +197,7 @@ def run_reference(args):
             "config": {"workload": "512x512 rays x 64 samples: inverse-LBS + SDF MLP (configs[1])",
                        "sample": f"{rays} rays x 64 samples per step (bounded sample of the frame)"},
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
-                             "sample": f"{rays} rays x 64 samples, torch CPU fp32, {threads} threads (fastest of 8/16/32/64/all)"},
+                             "sample": f"{rays} rays x 64 samples, torch CPU fp32, {threads} threads (fastest of 8/16/32/64)"},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -229,13 +259,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mode", default=os.environ.get("RECMV_BENCH_MODE", "tc3"), choices=sorted(MODES))
+    ap.add_argument("--scaling", default=os.environ.get("RECMV_BENCH_SCALING", "strong"), choices=("strong", "weak"),
+                    help="N > 1: strong = the SAME job (--frames 512x512x64 frames) row-sharded over the ranks with a "
+                         "flat gradient all-reduce per step (default); weak = one full frame per rank, no collective")
+    ap.add_argument("--frames", type=int, default=1, help="frames per step of the strong-scaling job (4 = configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     from recmv_b200 import ops, synth
-    from recmv_b200.render import SdfRenderer
+    from recmv_b200.render import SdfRenderer, shard_rows
     import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
@@ -248,69 +283,127 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
+    strong = args.scaling == "strong"
+    frames = max(args.frames, 1) if strong else 1
 
-    # ---- scene: weak scaling, every rank renders its own full 512x512 frame (its own pose) ----------
+    # ---- scene -------------------------------------------------------------------------------------------
+    # strong: ONE job of `frames` 512x512 frames; every rank renders a contiguous block of image rows of every
+    #         frame (render.shard_rows), weights / voxel / bone matrices replicated; per step one flat
+    #         fp32 all-reduce of the SDF-MLP gradient bucket (1 975 220 floats) on a side stream.
+    # weak:   every rank renders its own full frame (its own pose), no collective.
     mode = MODES[args.mode]
     ren = SdfRenderer(dev, mode=mode, samples=S)
-    poses, trans = synth.poses_trans(world, seed=11, device="cpu")
-    A, t = ren.bone_matrices(poses[rank:rank + 1].to(dev), trans[rank:rank + 1].to(dev))
-    dirs = synth.pinhole_rays(H, W, device=dev)
+    if strong:
+        poses, trans = synth.poses_trans(frames, seed=11, device="cpu")
+        A, t = ren.bone_matrices(poses.to(dev), trans.to(dev))
+        row0, rows = shard_rows(H, rank, world)
+        d1 = synth.pinhole_rays(H, W, device=dev, row0=row0, rows=rows)
+        dirs = d1.repeat(frames, 1).contiguous()          # frame-major: rays of frame f = [f*rows*W, (f+1)*rows*W)
+        rays_per_frame = rows * W
+        total_rays = frames * H * W
+    else:
+        poses, trans = synth.poses_trans(world, seed=11, device="cpu")
+        A, t = ren.bone_matrices(poses[rank:rank + 1].to(dev), trans[rank:rank + 1].to(dev))
+        dirs = synth.pinhole_rays(H, W, device=dev)
+        rays_per_frame = dirs.shape[0]
+        total_rays = world * H * W
     R = dirs.shape[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # gradient bucket of the SDF network (synthetic values; the all-reduce is the real collective of a training step)
+    n_grad = sum(p.numel() for p in ren.sdf_net.parameters())
+    grad_bucket = torch.randn(n_grad, device=dev, generator=torch.Generator(device=dev).manual_seed(5 + rank))
+    comm = torch.cuda.Stream(dev) if world > 1 else None
+    use_coll = world > 1 and strong
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def step_device():
+        """One step with inputs resident in HBM: [all-reduce of the gradient bucket on the side stream ||] render."""
+        work = None
+        if use_coll:
+            comm.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(comm):
+                work = dist.all_reduce(grad_bucket, op=dist.ReduceOp.SUM, async_op=True)
+        out = ren.render(dirs, A, t, rays_per_frame=rays_per_frame)
+        if work is not None:
+            work.wait()
+            torch.cuda.current_stream(dev).wait_stream(comm)
+        return out
+
+    def max_over_ranks(x):
+        tt = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     # ---- value: inputs resident in HBM ---------------------------------------------------------------
     for _ in range(warmup):
-        ren.render(dirs, A, t)
+        step_device()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ops.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    t0 = time.perf_counter()
+    t_beg.record()
     for i in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations (inside the bracket, ~0.05 ms)
         ev[i][0].record()
-        sdf, _, hit_idx, hit_t = ren.render(dirs, A, t)
+        sdf, _, hit_idx, hit_t = step_device()
         ev[i][1].record()
+    t_end.record()
     barrier()
-    wall = time.perf_counter() - t0
     launches = ops.launch_count() - launches0
     ops.check_async_errors()
     sampler.stop_flag = True
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    tt = torch.tensor([wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    wall_max = float(tt.item())
-    ms_per_step = wall_max * 1e3 / args.steps
-    value = world * R / (wall_max / args.steps)
-    kernel_ms = sum(step_ms) / len(step_ms)  # device time of the render launch sequence per step
+    dev_s = max_over_ranks(t_beg.elapsed_time(t_end) * 1e-3)   # device time of the K steps, max over ranks
+    ms_per_step = dev_s * 1e3 / args.steps
+    value = total_rays / (dev_s / args.steps)
+    kernel_ms = sum(step_ms) / len(step_ms)  # device time of one step's launch sequence on this rank
     nhit = int((hit_idx >= 0).sum().item())
+    comm_ok = None
+    if use_coll:   # the reduced bucket must be the same on every rank (sum of the per-rank seeds' buckets)
+        chk = torch.stack([grad_bucket[:1024].double().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        comm_ok = bool((lo == hi).all().item()) and bool(torch.isfinite(chk).all().item())
 
     # ---- e2e: HOST buffers in / HOST result out through the public call ---------------------------------
     dirs_h = dirs.cpu().pin_memory()
     A_h, t_h = A.cpu().pin_memory(), t.cpu().pin_memory()
     o_t = torch.empty(R, dtype=torch.float32).pin_memory()
     o_i = torch.empty(R, dtype=torch.int32).pin_memory()
+    grad_h = grad_bucket.cpu().pin_memory() if use_coll else None
+
+    def step_host():
+        work = None
+        if use_coll:   # gradients arrive from the host side too in this leg (H2D counted below)
+            with torch.cuda.stream(comm):
+                grad_bucket.copy_(grad_h, non_blocking=True)
+                work = dist.all_reduce(grad_bucket, op=dist.ReduceOp.SUM, async_op=True)
+        ren.render_host(dirs_h, A_h, t_h, o_t, o_i, rays_per_frame=rays_per_frame)
+        if work is not None:
+            work.wait()
+            torch.cuda.current_stream(dev).wait_stream(comm)
+        torch.cuda.current_stream(dev).synchronize()  # the host result must be readable every step
+
     for _ in range(2):
-        ren.render_host(dirs_h, A_h, t_h, o_t, o_i)
+        step_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ren.render_host(dirs_h, A_h, t_h, o_t, o_i)
-        torch.cuda.current_stream(dev).synchronize()  # the host result must be readable every step
+        step_host()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)   # host clock: the region ends when the HOST holds the result
     barrier()
-    tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e = world * R / (float(tt.item()) / args.steps)
-    h2d = dirs_h.numel() * 4 + A_h.numel() * 4 + t_h.numel() * 4
+    e2e = total_rays / (e2e_s / args.steps)
+    h2d = dirs_h.numel() * 4 + A_h.numel() * 4 + t_h.numel() * 4 + (grad_h.numel() * 4 if use_coll else 0)
     d2h = o_t.numel() * 4 + o_i.numel() * 4
 
     # ---- second half of the BASELINE metric: marching-cubes cells/s on a 257^3 grid (256^3 cells) -----------
@@ -331,11 +424,11 @@ def main():
         mc_bytes = 4 * 257 ** 3 + 12 * v.shape[0] + 24 * f.shape[0]   # SURVEY 8d algorithmic bytes
         mc = {"cells_per_s": 256 ** 3 / (mc_ms * 1e-3), "ms_per_call": mc_ms, "grid": "257^3", "verts": int(v.shape[0]),
               "faces": int(f.shape[0]), "algorithmic_bytes": mc_bytes,
-              "note": "count + scan + D2H of (V,F) + allocate + vertex + face passes, end to end per call"}
+              "note": "classify + count + scan + emit, end to end per call (device-resident counts)"}
 
     # ---- the other networks of the path on the same engine (reported next to the headline, not part of it) -----------
     secondary = None
-    if rank == 0 and world == 1 and mode != 0:
+    if rank == 0 and world == 1 and mode != 0 and not args.no_secondary:
         secondary = secondary_rates(dev, ren, mode)
 
     if rank == 0:
@@ -345,37 +438,49 @@ def main():
         ach = flop / (kernel_ms * 1e-3) / 1e12
         issued = {0: None, 1: 3, 2: 1}[mode]
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": TRAFFIC_BYTES.get(args.mode), "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": TRAFFIC_BYTES.get(args.mode) if world == 1 else None,
+                "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "kernel_ms": kernel_ms, "algorithmic_flop_per_launch": flop,
                 "mma_passes": issued,
                 "issued_frac": (ach * issued / peak_tf) if issued else None,
                 "note": "frac = ALGORITHMIC fp32-equivalent FLOP/s over dense-bf16 peak; tc3 issues 3 fp16 MMAs "
-                        "per product to meet the 1e-4 fp32 parity bar, so frac <= 1/3 by construction; "
+                        "per product to meet the fp32 parity bar, so frac <= 1/3 by construction; "
                         "issued_frac = tensor-pipe work actually issued over the same peak"}
         cpu = None
         if not args.no_cpu_baseline and world == 1:   # reported at N=1 only
             threads = best_cpu_threads()
-            rays = 4096
+            rays = 2048
             step = cpu_port_rate(rays, threads)
             step()
             c0 = time.perf_counter()
             n = 0
-            while time.perf_counter() - c0 < 12.0 or n < 2:
+            while time.perf_counter() - c0 < 10.0 or n < 2:
                 step()
                 n += 1
             cdt = (time.perf_counter() - c0) / n
             cpu = {"value": rays / cdt, "unit": "rays/s", "cores": threads, "kind": "port",
                    "sample": f"{rays} rays x 64 samples x {n} reps (oracle torch-CPU restatement of inverse-LBS + "
-                             f"SDF MLP, fp32; {threads} threads = fastest of 8/16/32/64/all on this host)"}
+                             f"SDF MLP, fp32; {threads} threads = fastest of 8/16/32/64 on this host)"}
+        if strong:
+            workload = (f"configs[1]: {frames} frame(s) of 512x512 rays x 64 samples/ray, 9-layer x512 SDF MLP "
+                        "(PeopleSnapshot-shaped synthetic scene), inverse-LBS on a 24x65x225x129 skinning voxel"
+                        + (f"; image rows sharded over {world} ranks, one flat fp32 all-reduce of the SDF-MLP gradient "
+                           f"bucket ({n_grad} floats) per step on a side stream" if world > 1 else ""))
+        else:
+            workload = ("configs[1]: 512x512 rays x 64 samples/ray, 9-layer x512 SDF MLP (PeopleSnapshot-shaped "
+                        "synthetic scene), inverse-LBS on a 24x65x225x129 skinning voxel, one frame per GPU")
         line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong" if strong else "weak",
                 "vs_baseline": None, "dtype": {0: "f32", 1: "f16x3->f32", 2: "f16->f32"}[mode],
                 "data": "synthetic",
-                "config": {"workload": "configs[1]: 512x512 rays x 64 samples/ray, 9-layer x512 SDF MLP "
-                                       "(PeopleSnapshot-shaped synthetic scene), inverse-LBS on a "
-                                       "24x65x225x129 skinning voxel, one frame per GPU",
-                           "mlp_mode": args.mode, "rays_per_gpu": R, "samples_per_ray": S,
+                "config": {"workload": workload,
+                           "mlp_mode": args.mode, "rays_per_gpu": R, "samples_per_ray": S, "frames": frames,
                            "l2": "256 MiB buffer written between timed steps (inside the bracket)",
+                           "timing": "CUDA events around the K steps on the launching stream, max over ranks",
+                           "collective": ({"op": "all_reduce(sum, fp32)", "bytes": 4 * n_grad, "backend": "nccl",
+                                           "inside_timed_region": True, "result_identical_on_all_ranks": comm_ok}
+                                          if use_coll else None),
                            "hits": nhit},
                 "clocks": sampler.summary(), "gpu_launches": launches,
                 "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -122,6 +122,13 @@ RECMV_API int recmv_lbs_inverse(const float* x_obs, const float* A, const float*
                       const recmv_voxel_t* vox /*host*/, float* x_can, uint8_t* valid, int64_t P,
                       recmv_stream_t stream);
 
+/* Bone matrices of the SMPL kinematic chain: replaces the 24-joint python loop of model/Deformer.py:372-405 (and
+ * posedSkeleton, :305-326) when no autograd graph is needed.  poses [F,24,3] axis-angle, Js [24,3], parents [24] int32
+ * (device), init_pose [24,4,4] or NULL (Deformer.py:397-404).  G [F,24,4,4] = chained joint transforms (always
+ * written; G[:,:,:3,3] is the posed skeleton), A [F,24,4,4] = G . init_pose (may be NULL).                       */
+RECMV_API int recmv_bone_matrices(const float* poses, const float* Js, const int* parents, const float* init_pose,
+                        float* G, float* A, int num_frames, recmv_stream_t stream);
+
 /* ---- A1+A2: Embedder + ImplicitNetwork.forward -------------------------------------------------
  * replaces model/Embedder.py:43-50 + model/network.py:89-119 (+ utils/utils.py:40-46 weights).
  * Network shape is the reference's getTmpSdf: PE(6) 39 -> 512 x3 -> 473 (+39 skip)/sqrt2 -> 512 x4

@@ -56,6 +56,7 @@ SIGNATURES = {
                               POINTER(Voxel), c_void_p, c_void_p, c_int64, c_void_p]),
     "recmv_lbs_inverse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                   POINTER(Voxel), c_void_p, c_void_p, c_int64, c_void_p]),
+    "recmv_bone_matrices": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "recmv_sdf_packed_bytes": (c_size_t, []),
     "recmv_sdf_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "recmv_sdf_mlp_fwd": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int64,

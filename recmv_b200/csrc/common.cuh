@@ -21,10 +21,11 @@ inline int launch_status() {
 }
 
 inline int num_sms() {
-  static int n = 0;
+  static int cached[16] = {0};   // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cached[dev & 15];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }

@@ -67,6 +67,78 @@ __global__ void __launch_bounds__(128) lbs_inverse_kernel(const float* __restric
   }
 }
 
+
+// Bone matrices A = G . init_pose of the SMPL kinematic chain (model/Deformer.py:372-405): axis-angle -> rotation
+// (the un-vendored smpl_pytorch.util.batch_rodrigues, standard HMR quaternion form: angle = |theta + 1e-8|), chain
+// G_i = G_parent(i) . [R_i | J_i - J_parent(i)], then A_i = G_i . init_pose_i (or G_i - [0 | G_i J_i] without an init
+// pose).  One thread per frame walks the 24 joints (parents precede children); replaces ~150 tiny torch launches
+// per call of LBSkinner.forward / .inverse when no autograd graph is needed.
+__global__ void __launch_bounds__(64) bone_matrices_kernel(const float* __restrict__ poses, const float* __restrict__ Js,
+                                                           const int* __restrict__ parents, const float* __restrict__ init_pose,
+                                                           float* __restrict__ G, float* __restrict__ A, int F) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float* g = G + (size_t)f * 24 * 16;
+  for (int i = 0; i < 24; ++i) {
+    const float* th = poses + ((size_t)f * 24 + i) * 3;
+    const float ax = th[0], ay = th[1], az = th[2];
+    const float bx = ax + 1e-8f, by = ay + 1e-8f, bz = az + 1e-8f;
+    const float angle = sqrtf(bx * bx + by * by + bz * bz);
+    const float half = angle * 0.5f;
+    float sn, cs;
+    sincosf(half, &sn, &cs);
+    float qw = cs, qx = sn * (ax / angle), qy = sn * (ay / angle), qz = sn * (az / angle);
+    const float qn = sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+    qw /= qn; qx /= qn; qy /= qn; qz /= qn;
+    const float w2 = qw * qw, x2 = qx * qx, y2 = qy * qy, z2 = qz * qz;
+    const float wx = qw * qx, wy = qw * qy, wz = qw * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz;
+    float L[16];   // local transform [R | t; 0 0 0 1]
+    L[0] = w2 + x2 - y2 - z2; L[1] = 2 * xy - 2 * wz;   L[2] = 2 * wy + 2 * xz;
+    L[4] = 2 * wz + 2 * xy;   L[5] = w2 - x2 + y2 - z2; L[6] = 2 * yz - 2 * wx;
+    L[8] = 2 * xz - 2 * wy;   L[9] = 2 * wx + 2 * yz;   L[10] = w2 - x2 - y2 + z2;
+    const int par = i == 0 ? -1 : parents[i];
+    L[3] = Js[3 * i] - (par >= 0 ? Js[3 * par] : 0.f);
+    L[7] = Js[3 * i + 1] - (par >= 0 ? Js[3 * par + 1] : 0.f);
+    L[11] = Js[3 * i + 2] - (par >= 0 ? Js[3 * par + 2] : 0.f);
+    L[12] = 0.f; L[13] = 0.f; L[14] = 0.f; L[15] = 1.f;
+    float* gi = g + 16 * i;
+    if (par < 0) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) gi[e] = L[e];
+    } else {
+      const float* gp = g + 16 * par;
+      float Pm[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) Pm[e] = gp[e];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          gi[4 * r + c] = Pm[4 * r] * L[c] + Pm[4 * r + 1] * L[4 + c] + Pm[4 * r + 2] * L[8 + c] + Pm[4 * r + 3] * L[12 + c];
+    }
+  }
+  if (!A) return;
+  for (int i = 0; i < 24; ++i) {
+    const float* gi = g + 16 * i;
+    float* a = A + ((size_t)f * 24 + i) * 16;
+    if (init_pose) {
+      const float* ip = init_pose + 16 * i;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          a[4 * r + c] = gi[4 * r] * ip[c] + gi[4 * r + 1] * ip[4 + c] + gi[4 * r + 2] * ip[8 + c] + gi[4 * r + 3] * ip[12 + c];
+    } else {
+      const float jx = Js[3 * i], jy = Js[3 * i + 1], jz = Js[3 * i + 2];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        a[4 * r] = gi[4 * r]; a[4 * r + 1] = gi[4 * r + 1]; a[4 * r + 2] = gi[4 * r + 2];
+        a[4 * r + 3] = gi[4 * r + 3] - (gi[4 * r] * jx + gi[4 * r + 1] * jy + gi[4 * r + 2] * jz);
+      }
+    }
+  }
+}
+
 static int lbs_check(const recmv_voxel_t* vox, int nf, int64_t P) {
   if (!vox || !vox->ws_cl) return RECMV_E_NULL;
   if (vox->D <= 0 || vox->H <= 0 || vox->W <= 0 || nf <= 0 || P < 0) return RECMV_E_SHAPE;
@@ -103,5 +175,15 @@ extern "C" int recmv_lbs_inverse(const float* x_obs, const float* A, const float
   int g = stride_grid(P, 128, 8);
   lbs_inverse_kernel<<<g, 128, 0, (cudaStream_t)stream>>>(x_obs, A, trans, batch_inds, points_per_frame,
                                                           num_frames, to_voxel(vox), x_can, valid, P);
+  return launch_status();
+}
+
+extern "C" int recmv_bone_matrices(const float* poses, const float* Js, const int* parents, const float* init_pose,
+                                   float* G, float* A, int num_frames, recmv_stream_t stream) {
+  if (num_frames < 0) return RECMV_E_SHAPE;
+  if (num_frames == 0) return RECMV_OK;
+  if (!poses || !Js || !parents || !G) return RECMV_E_NULL;
+  bone_matrices_kernel<<<(num_frames + 63) / 64, 64, 0, (cudaStream_t)stream>>>(poses, Js, parents, init_pose, G, A,
+                                                                                num_frames);
   return launch_status();
 }

@@ -57,6 +57,10 @@ int simt_sdf_forward(const PointSource& src, const void* packed, const PeWeights
 int tc_sdf_forward(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
                    float* out_feat, int64_t P, int passes, cudaStream_t st);
 
+// the per-device status record (mapped pinned host memory) the tcgen05 kernels report into: bounded-wait
+// time-outs (code 1) and fp16 operand-range violations (code 2); see recmv_check_async_errors
+int device_status_record(void** out);
+
 // value + input gradient in one forward-mode launch (tcgen05 path only)
 int tc_sdf_forward_grad(const float* x, const void* packed, const PeWeights& pw, float* out_sdf, float* out_feat,
                         float* out_grad, int64_t P, int passes, cudaStream_t st);

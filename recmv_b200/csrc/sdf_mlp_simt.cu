@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) pack_layer_kernel(const float* __restrict
                                                          const float* __restrict__ b, int l, int out,
                                                          int in, float* __restrict__ w32t, int npad32,
                                                          float* __restrict__ bpad,
-                                                         __half* __restrict__ planes) {
+                                                         __half* __restrict__ planes, int* __restrict__ status /*DevStatus*/) {
   const float scale = (l == 4) ? 0.70710678118654752440f : 1.f;  // cat([x, pe]) / sqrt(2) folded in
   const int np = num_panels(l);
   int64_t total = (int64_t)np * 512 * 64;
@@ -48,7 +48,12 @@ __global__ void __launch_bounds__(256) pack_layer_kernel(const float* __restrict
     else if (l == 4) src_k = pi < 8 ? (pi * 64 + kk < kSkipOut ? pi * 64 + kk : -1) : (kk < kPE ? kSkipOut + kk : -1);
     else src_k = pi * 64 + kk;
     float v = (n < out && src_k >= 0) ? W[(size_t)n * in + src_k] * scale : 0.f;
-    const float vs = v * kWgtScale;
+    float vs = v * kWgtScale;
+    if (!(fabsf(vs) < 65504.f)) {   // |w| >= 63.97: outside the tcgen05 operand range -> status code 2 (tc_common.cuh)
+      volatile int* st = status;
+      if (st[0] == 0) { st[1] = 1201; st[2] = blockIdx.x; __threadfence_system(); st[0] = 2; }
+      vs = fminf(fmaxf(vs, -65504.f), 65504.f);
+    }
     __half h = __float2half_rn(vs);
     size_t o = ((size_t)(panel_base(l) + pi) * 512 + n) * 64 + kk;
     planes[o] = h;
@@ -205,11 +210,13 @@ int simt_sdf_forward(const PointSource& src, const void* packed, const PeWeights
     w.b[l] = (const float*)((const char*)packed + L.b32_off[l]);
   }
   size_t smem = (size_t)(2 * kTileM * kLd + kTileM * 40) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[16] = {false};   // the opt-in is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 15]) {
     cudaError_t e = cudaFuncSetAttribute(sdf_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_done = true;
+    attr_done[dev & 15] = true;
   }
   int64_t tiles = (P + kTileM - 1) / kTileM;
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
@@ -263,12 +270,15 @@ extern "C" int recmv_sdf_pack_weights(const float* W_all, const float* b_all, vo
   PackedLayout L = packed_layout();
   cudaStream_t st = (cudaStream_t)stream;
   size_t woff = 0, boff = 0;
+  void* sd = nullptr;
+  int s0 = device_status_record(&sd);
+  if (s0) return s0;
   for (int l = 0; l < kNumLayers; ++l) {
     int in = layer_in(l), out = layer_out(l);
     char* base = (char*)packed;
     pack_layer_kernel<<<stride_grid((int64_t)num_panels(l) * 512 * 64, 256, 4), 256, 0, st>>>(
         W_all + woff, b_all + boff, l, out, in, (float*)(base + L.w32_off[l]), kNpad32(l),
-        (float*)(base + L.b32_off[l]), (__half*)(base + L.f16_off));
+        (float*)(base + L.b32_off[l]), (__half*)(base + L.f16_off), (int*)sd);
     int s = launch_status();
     if (s) return s;
     woff += (size_t)in * out;

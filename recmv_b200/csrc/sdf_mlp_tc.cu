@@ -531,6 +531,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                   for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f) * kActScale;   // ReLU (deformer)
                 }
               }
+              range_check8(v, prm.status, 1000 + l);
               uint4 hi, lo;
               split8(v, hi, lo);
               const int kb = f >> 6, chunk = (f & 63) >> 3;
@@ -698,6 +699,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] *= kActScale;
+          range_check8(v, prm.status, 1100);
           uint4 hi, lo;
           split8(v, hi, lo);
           const uint32_t off = (uint32_t)(chunk >> 3) * 8192u + sw128_offset(row, chunk & 7);
@@ -731,6 +733,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         if (it > 0) mbar_wait(BAR(kBarPeFree), (uint32_t)((it - 1) & 1), abort_flag, prm.status, 400);
 #pragma unroll
         for (int chunk = 0; chunk < 5; ++chunk) {          // columns 0..39
+          range_check8(head + 8 * chunk, prm.status, 1101);
           uint4 hi, lo;
           split8(head + 8 * chunk, hi, lo);
           const uint32_t off = sw128_offset(row, chunk);
@@ -745,6 +748,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
             const int ci = 8 * chunk + e - 39;             // index into the condition vector
             v[e] = (live && value_row && ci < 128) ? __ldg(cond + ci) * kActScale : 0.f;
           }
+          range_check8(v, prm.status, 1102);
           uint4 hi, lo;
           split8(v, hi, lo);
           const uint32_t off = (uint32_t)(chunk >> 3) * 8192u + sw128_offset(row, chunk & 7);
@@ -773,7 +777,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
 #pragma unroll
       for (int chunk = 0; chunk < 8; ++chunk) {
         uint4 hi = zero, lo = zero;
-        if (chunk < 5) split8(pe + 8 * chunk, hi, lo);
+        if (chunk < 5) { range_check8(pe + 8 * chunk, prm.status, 1103); split8(pe + 8 * chunk, hi, lo); }
         const uint32_t off = sw128_offset(row, chunk);
         st_shared_v4(base + kOffPeHi + off, hi);
         st_shared_v4(base + kOffPeLo + off, lo);
@@ -807,6 +811,17 @@ float g_acc_gain_kb[2] = {4.f * 5.9604645e-8f, 4.f * 5.9604645e-8f};
 inline void set_acc_scales(TcParams& prm) { prm.acc_gain_kb = g_acc_gain_kb[prm.passes == 3 ? 0 : 1]; }
 
 // one mapped, pinned status record per device
+int tc_status_record(int dev, DevStatus** out);
+}  // namespace
+int device_status_record(void** out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevStatus* sd = nullptr;
+  int s = tc_status_record(dev, &sd);
+  *out = sd;
+  return s;
+}
+namespace {
 int tc_status_record(int dev, DevStatus** out) {
   DevStatus*& h = g_status_host[dev & 15];
   if (!h) {
@@ -948,12 +963,13 @@ DeformLayout deform_layout() {
 __global__ void __launch_bounds__(256) pack_plain_layer_kernel(const float* __restrict__ W, const float* __restrict__ b,
                                                                int out, int in, int pbase, int npanels,
                                                                float* __restrict__ bpad, __half* __restrict__ planes,
-                                                               int total_panels) {
+                                                               int total_panels, DevStatus* status) {
   int64_t total = (int64_t)npanels * 512 * 64;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int pi = (int)(i / (512 * 64)), n = (int)((i / 64) % 512), kk = (int)(i % 64);
     const int k = pi * 64 + kk;
-    const float v = (n < out && k < in) ? W[(size_t)n * in + k] * kWgtScale : 0.f;
+    float v = (n < out && k < in) ? W[(size_t)n * in + k] * kWgtScale : 0.f;
+    if (!(fabsf(v) < 65504.f)) { report_range(status, 1200); v = fminf(fmaxf(v, -65504.f), 65504.f); }
     const __half h = __float2half_rn(v);
     const size_t o = ((size_t)(pbase + pi) * 512 + n) * 64 + kk;
     planes[o] = h;
@@ -974,10 +990,13 @@ extern "C" int recmv_translator_pack_weights(const float* W_all, const float* b_
   DeformLayout L = deform_layout();
   char* base = (char*)packed;
   size_t woff = 0, boff = 0;
+  void* sd = nullptr;
+  int s0 = device_status_record(&sd);
+  if (s0) return s0;
   for (int l = 0; l < kDefLayers; ++l) {
     pack_plain_layer_kernel<<<stride_grid((int64_t)def_npanels(l) * 512 * 64, 256, 4), 256, 0, (cudaStream_t)stream>>>(
         W_all + woff, b_all + boff, def_out(l), def_in(l), def_pbase(l), def_npanels(l),
-        (float*)(base + L.bias_off) + l * 512, (__half*)(base + L.f16_off), kDefPanels);
+        (float*)(base + L.bias_off) + l * 512, (__half*)(base + L.f16_off), kDefPanels, (DevStatus*)sd);
     int s = launch_status();
     if (s) return s;
     woff += (size_t)def_in(l) * def_out(l);
@@ -1087,10 +1106,13 @@ extern "C" int recmv_rendernet_pack_weights(const float* W_all, const float* b_a
   DeformLayout L = rgb_layout();
   char* base = (char*)packed;
   size_t woff = 0, boff = 0;
+  void* sd = nullptr;
+  int s0 = device_status_record(&sd);
+  if (s0) return s0;
   for (int l = 0; l < kRgbLayers; ++l) {
     pack_plain_layer_kernel<<<stride_grid((int64_t)rgb_npanels(l) * 512 * 64, 256, 4), 256, 0, (cudaStream_t)stream>>>(
         W_all + woff, b_all + boff, rgb_out(l), rgb_in(l), rgb_pbase(l), rgb_npanels(l),
-        (float*)(base + L.bias_off) + l * 512, (__half*)(base + L.f16_off), kRgbPanels);
+        (float*)(base + L.bias_off) + l * 512, (__half*)(base + L.f16_off), kRgbPanels, (DevStatus*)sd);
     int s = launch_status();
     if (s) return s;
     woff += (size_t)rgb_in(l) * rgb_out(l);

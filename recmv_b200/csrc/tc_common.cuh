@@ -185,10 +185,30 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
 // fp32 -> fp16 hi/lo split of 8 consecutive K values, packed for one 16-byte store each.
 // cvt.rn.f16x2.f32 packs two conversions into one ALU-pipe instruction (F2FP.PACK_AB); the scalar
 // __float2half_rn path compiles to F2F on the quarter-rate XU pipe, which made the epilogue XU-bound.
+// .satfinite: an operand beyond fp16's range saturates to +-65504 instead of becoming inf (hi = inf would make
+// lo = v - inf = -inf and the MMA NaN); the writers below additionally raise the overflow status (range_check8).
 __device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
   uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
+}
+// Operand range of the tcgen05 path: scaled activations (2^6 a) and weights (2^10 w) must stay below fp16's
+// 65504, i.e. |a| < 1023.5, |w| < 63.97.  The reference's fp32 has no such limit, so a violation is REPORTED
+// (status code 2 in the mapped record -> recmv_check_async_errors / RECMV_E_DEVICE), never silent.
+constexpr int kStatusTimeout = 1, kStatusRange = 2;
+__device__ __forceinline__ void report_range(DevStatus* status, int tag) {
+  volatile DevStatus* vs = status;
+  if (vs->code == 0) {
+    vs->detail = tag;
+    vs->block = blockIdx.x;
+    __threadfence_system();
+    vs->code = kStatusRange;
+  }
+}
+__device__ __forceinline__ void range_check8(const float v[8], DevStatus* status, int tag) {
+  const float m = fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))),
+                        fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7]))));
+  if (!(m < 65504.f)) report_range(status, tag);   // also catches NaN
 }
 __device__ __forceinline__ void split8(const float v[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];

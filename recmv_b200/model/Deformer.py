@@ -77,8 +77,7 @@ class CompositeDeformer(nn.Module):
         with torch.no_grad():
             A = sk.bone_matrices(poses)
             t = trans + sk.extra_trans
-        center = sk.bbox_center.view(-1)[:3].tolist()
-        extend = float(sk.bbox_extend.view(-1)[0])
+        center, extend = sk.bbox_host()
         return (tr.packed_weights(), ratio_to_weights(tr.multires, ratio['deformerRatio']), conds[0],
                 (A, t, sk.ws_channels_last(), center, extend), tr.mlp_mode)
 
@@ -95,8 +94,7 @@ class CompositeDeformer(nn.Module):
         if not want_jacobian and torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
             return None
         A = sk.bone_matrices(poses)
-        center = sk.bbox_center.view(-1)[:3].tolist()
-        extend = float(sk.bbox_extend.view(-1)[0])
+        center, extend = sk.bbox_host()
         ratio = kwargs['ratio']['deformerRatio']
         ppf = 0 if batch_inds is not None else ps.shape[1]
         res = ops.deformer_forward(ps.reshape(-1, 3), conds[0], tr.packed_weights(),
@@ -222,6 +220,8 @@ class LBSkinner(nn.Module):
                 self.register_buffer('init_pose', init_pose.view(24, 4, 4))
         self._ws_cl = None
         self._ws_key = None
+        self._bbox_key, self._bbox_host = None, None
+        self._parents_i32 = None
         self.last_path = None
 
     def bbox_size(self):
@@ -261,8 +261,25 @@ class LBSkinner(nn.Module):
             results.append(torch.matmul(results[int(parent[i])], make_A(R[:, i], Js[:, i] - Js[:, int(parent[i])])))
         return torch.stack(results, dim=1), Js
 
+    def bbox_host(self):
+        """(center [3] floats, extend float) of the voxel normalisation as HOST values, cached against the buffers'
+        (data_ptr, _version): the kernels take them by value, and reading CUDA buffers per call would cost two
+        blocking D2H syncs on every deformer launch."""
+        key = (self.bbox_center.data_ptr(), self.bbox_center._version, self.bbox_extend.data_ptr(), self.bbox_extend._version)
+        if self._bbox_key != key:
+            self._bbox_host = (self.bbox_center.view(-1)[:3].tolist(), float(self.bbox_extend.view(-1)[0]))
+            self._bbox_key = key
+        return self._bbox_host
+
+    def _parents_dev(self, device):
+        if self._parents_i32 is None or self._parents_i32.device != device:
+            self._parents_i32 = torch.as_tensor(self.parents).to(torch.int32).to(device).contiguous()
+        return self._parents_i32
+
     def bone_matrices(self, poses):
-        """A [N,24,4,4] = G . init_pose (Deformer.py:372-405)."""
+        """A [N,24,4,4] = G . init_pose (Deformer.py:372-405).  One kernel when no graph is needed."""
+        if poses.is_cuda and not (torch.is_grad_enabled() and poses.requires_grad):
+            return ops.bone_matrices(poses.reshape(-1, 24, 3), self.Js, self._parents_dev(poses.device), self.init_pose)[1]
         results, Js = self._chain(poses)
         batch_size = poses.shape[0]
         if self.init_pose is None:
@@ -274,6 +291,9 @@ class LBSkinner(nn.Module):
     def posedSkeleton(self, conds):
         poses, trans = conds
         assert (poses.shape[0] == trans.shape[0])
+        if poses.is_cuda and not (torch.is_grad_enabled() and poses.requires_grad):
+            G, _ = ops.bone_matrices(poses.reshape(-1, 24, 3), self.Js, self._parents_dev(poses.device), None, want_A=False)
+            return G[:, :, :3, 3]
         results, _ = self._chain(poses)
         return results[:, :, :3, 3]
 
@@ -292,13 +312,46 @@ class LBSkinner(nn.Module):
             self._ws_key = key
         return self._ws_cl
 
+    # ColorBrewer "Paired" entries 1 / 3 / 5 (what matplotlib's get_cmap('Paired').colors holds) and white, per
+    # joint: engineer/utils/skinning_weights.py:5-52
+    _JOINT_COLORS = None
+
+    def query_skinning_weights_colors(self, tps):
+        """model/Deformer.py:331-340: per-point colour = skinning weights [P,24] x fixed joint colours; CPU float64
+        tensor [P,3] like the reference (torch CPU weights times a float64 numpy table)."""
+        if LBSkinner._JOINT_COLORS is None:
+            blue, green, red, white = (31 / 255, 120 / 255, 180 / 255), (51 / 255, 160 / 255, 44 / 255), \
+                (227 / 255, 26 / 255, 28 / 255), (1.0, 1.0, 1.0)
+            names = "w b g r w w w g b r w w w b g r g b w w b g w w".split()   # cyan -> Paired[3], darkgreen -> Paired[1]
+            LBSkinner._JOINT_COLORS = torch.tensor([{"w": white, "b": blue, "g": green, "r": red}[n] for n in names],
+                                                   dtype=torch.float64)
+        pts = tps.reshape(-1, 3)
+        if pts.is_cuda:
+            with torch.no_grad():
+                center, extend = self.bbox_host()
+                ident = torch.eye(4, device=pts.device).expand(1, 24, 4, 4).contiguous()
+                _, w = ops.lbs_forward(pts, ident, torch.zeros((1, 3), device=pts.device), self.ws_channels_last(),
+                                       center, extend, None, pts.shape[0], None, want_weights=True)
+        else:
+            raise RuntimeError("recmv_b200.LBSkinner runs on CUDA tensors only (no CPU path)")
+        return (w.detach().cpu().double()[:, :, None] * LBSkinner._JOINT_COLORS[None]).sum(1)
+
+    def repose(self, ps, conds, batch_inds=None, **kwargs):
+        """model/Deformer.py:446-531: `forward` without the extra translation (used when re-posing canonical
+        geometry for animation)."""
+        return self._warp(ps, conds, batch_inds, add_extra=False)
+
     def forward(self, ps, conds, batch_inds=None, **kwargs):
+        return self._warp(ps, conds, batch_inds, add_extra=True)
+
+    def _warp(self, ps, conds, batch_inds, add_extra):
         if type(ps) == list:
             tps, ps = ps
         else:
             tps = ps
         poses, trans = conds
-        trans = trans + self.extra_trans
+        if add_extra:
+            trans = trans + self.extra_trans
         batch_size = poses.shape[0]
         assert (batch_size == trans.shape[0])
         A = self.bone_matrices(poses)
@@ -306,8 +359,7 @@ class LBSkinner(nn.Module):
             t.requires_grad for t in (ps, tps, poses, trans))
         if not ps.is_cuda:
             raise RuntimeError("recmv_b200.LBSkinner runs on CUDA tensors only (no CPU path)")
-        center = self.bbox_center.view(-1)[:3].tolist()
-        extend = float(self.bbox_extend.view(-1)[0])
+        center, extend = self.bbox_host()
         if not needs_graph:
             self.last_path = "fused"
             if batch_inds is None:
@@ -337,8 +389,7 @@ class LBSkinner(nn.Module):
         poses, trans = conds
         trans = trans + self.extra_trans
         A = self.bone_matrices(poses)
-        center = self.bbox_center.view(-1)[:3].tolist()
-        extend = float(self.bbox_extend.view(-1)[0])
+        center, extend = self.bbox_host()
         shp = x_obs.shape
         ppf = 0 if batch_inds is not None else (x_obs.shape[1] if x_obs.dim() == 3 else x_obs.shape[0])
         xc, ok = ops.lbs_inverse(x_obs.reshape(-1, 3), A, trans, self.ws_channels_last(), center, extend,

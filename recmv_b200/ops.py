@@ -301,6 +301,21 @@ def lbs_inverse(x_obs, A, trans, ws_cl, center, extend, batch_inds=None, points_
     return xc, valid.view(torch.bool)
 
 
+def bone_matrices(poses, Js, parents_i32, init_pose=None, want_A=True):
+    """(G [F,24,4,4], A [F,24,4,4] or None): the kinematic chain of LBSkinner in one launch (no autograd)."""
+    poses = poses.detach().contiguous().float()
+    _check_input(poses, "poses")
+    F_ = poses.shape[0]
+    dev = poses.device
+    G = torch.empty((F_, 24, 4, 4), dtype=torch.float32, device=dev)
+    A = torch.empty((F_, 24, 4, 4), dtype=torch.float32, device=dev) if want_A else None
+    ip = init_pose.contiguous().float() if init_pose is not None else None
+    with torch.cuda.device(dev):
+        check(_lib.load().recmv_bone_matrices(_ptr(poses), _ptr(Js.contiguous().float()), _ptr(parents_i32), _ptr(ip),
+                                              _ptr(G), _ptr(A), F_, _stream(poses)), "recmv_bone_matrices")
+    return G, A
+
+
 # --------------------------------------------------------------------------------------------------
 # SDF MLP
 # --------------------------------------------------------------------------------------------------
@@ -598,6 +613,9 @@ def check_async_errors(clear=False):
     info = (ctypes.c_int * 3)()
     st = _lib.load().recmv_check_async_errors(info, 1 if clear else 0)
     if st != 0:
+        if info[0] == 2:
+            raise _lib.RecmvError(f"tcgen05 operand range exceeded (|activation| >= 1023.5 or |weight| >= 63.97 does not "
+                                  f"fit the scaled fp16 operands; results were saturated): site tag={info[1]} block={info[2]}")
         raise _lib.RecmvError(f"tcgen05 kernel aborted: code={info[0]} barrier tag={info[1]} block={info[2]}")
 
 

@@ -63,8 +63,13 @@ def allreduce_grads(params, group=None, comm_stream=None):
 
 
 class SdfRenderer:
+    """`sdf_net` / `skinner`: an existing `ImplicitNetwork` / `LBSkinner` pair (what `getOptNet` builds,
+    model/network.py:204-272) -- the renderer then marches THAT scene; without them a seeded synthetic scene of the
+    BASELINE shapes is fabricated (bench / tests).  The packed weight blob is fetched per call from the network's
+    version-keyed cache, so an optimizer step or `load_state_dict` between renders is picked up."""
+
     def __init__(self, device, sdf_net=None, voxel_shape=(65, 225, 129), seed=0, mode=None,
-                 samples=64, t_near=synth.T_NEAR, t_far=synth.T_FAR, cam_pos=synth.CAM_POS):
+                 samples=64, t_near=synth.T_NEAR, t_far=synth.T_FAR, cam_pos=synth.CAM_POS, skinner=None):
         self.device = torch.device(device)
         self.mode = ops.DEFAULT_MLP_MODE if mode is None else mode
         self.samples, self.t_near, self.t_far, self.cam_pos = samples, t_near, t_far, cam_pos
@@ -72,15 +77,26 @@ class SdfRenderer:
             torch.manual_seed(seed)
             sdf_net = getTmpSdf(self.device, 6, 0.6, 256)
         self.sdf_net = sdf_net
-        Js, parents, init = synth.skeleton()
-        ws = synth.skinning_voxel(voxel_shape, seed=7, device=self.device)
-        self.skinner = LBSkinner(ws, [-1.1] * 3, [1.1] * 3, Js, parents, init_pose=init,
-                                 bbox_extend=torch.tensor(synth.BBOX_EXTEND),
-                                 bbox_center=torch.tensor(synth.BBOX_CENTER)).to(self.device)
-        self.ws_cl = self.skinner.ws_channels_last()
-        self.packed = sdf_net.packed_weights()
+        if skinner is None:
+            Js, parents, init = synth.skeleton()
+            ws = synth.skinning_voxel(voxel_shape, seed=7, device=self.device)
+            skinner = LBSkinner(ws, [-1.1] * 3, [1.1] * 3, Js, parents, init_pose=init,
+                                bbox_extend=torch.tensor(synth.BBOX_EXTEND),
+                                bbox_center=torch.tensor(synth.BBOX_CENTER)).to(self.device)
+        self.skinner = skinner
         self.pe_w = [1.0] * 12
         self._sdf_buf = None
+
+    @property
+    def ws_cl(self):
+        return self.skinner.ws_channels_last()
+
+    @property
+    def packed(self):
+        return self.sdf_net.packed_weights()
+
+    def _bbox(self):
+        return self.skinner.bbox_host()
 
     def bone_matrices(self, poses, trans):
         with torch.no_grad():
@@ -92,16 +108,18 @@ class SdfRenderer:
         R = ray_dirs.shape[0]
         if self._sdf_buf is None or self._sdf_buf.shape[0] != R:
             self._sdf_buf = torch.empty((R, self.samples), dtype=torch.float32, device=self.device)
+        center, extend = self._bbox()
         return ops.render_sdf(ray_dirs, self.cam_pos, self.t_near, self.t_far, self.samples, A, trans,
-                              self.ws_cl, synth.BBOX_CENTER, synth.BBOX_EXTEND, self.packed, self.pe_w,
+                              self.ws_cl, center, extend, self.packed, self.pe_w,
                               self.mode, None, rays_per_frame or R, want_xc, True, self._sdf_buf)
 
-    def render_host(self, ray_dirs_pinned, A_pinned, trans_pinned, out_hit_t_pinned, out_hit_idx_pinned):
+    def render_host(self, ray_dirs_pinned, A_pinned, trans_pinned, out_hit_t_pinned, out_hit_idx_pinned,
+                    rays_per_frame=0):
         """End-to-end call on HOST buffers (pinned): H2D inputs, fused render, D2H per-ray result."""
         d = ray_dirs_pinned.to(self.device, non_blocking=True)
         A = A_pinned.to(self.device, non_blocking=True)
         t = trans_pinned.to(self.device, non_blocking=True)
-        _, _, hit_idx, hit_t = self.render(d, A, t)
+        _, _, hit_idx, hit_t = self.render(d, A, t, rays_per_frame=rays_per_frame)
         out_hit_t_pinned.copy_(hit_t, non_blocking=True)
         out_hit_idx_pinned.copy_(hit_idx, non_blocking=True)
         return out_hit_t_pinned, out_hit_idx_pinned
@@ -114,8 +132,9 @@ class SdfRenderer:
         the hit rays only).  Returns (hit mask [R], t [R], x_obs [R,3], x_can [R,3], sdf at the point [R])."""
         R = ray_dirs.shape[0]
         rpf = 0 if frame_of_ray is not None else R // max(int(A.shape[0]), 1)
+        center, extend = self._bbox()
         sdf, _, hit_idx, hit_t = ops.render_sdf(ray_dirs, self.cam_pos, self.t_near, self.t_far, self.samples, A,
-                                                trans, self.ws_cl, synth.BBOX_CENTER, synth.BBOX_EXTEND,
+                                                trans, self.ws_cl, center, extend,
                                                 self.packed, self.pe_w, self.mode, frame_of_ray, rpf, False, True)
         hit = hit_idx > 0
         idx = hit.nonzero(as_tuple=False).view(-1)
@@ -132,9 +151,9 @@ class SdfRenderer:
 
         def eval_at(t):
             xo = cam[None] + t[:, None] * d
-            xc, ok = ops.lbs_inverse(xo, A, trans, self.ws_cl, synth.BBOX_CENTER, synth.BBOX_EXTEND, frames, 0)
-            with torch.no_grad():
-                v = self.sdf_net(xc, None)[:, 0]
+            xc, ok = ops.lbs_inverse(xo, A, trans, self.ws_cl, center, extend, frames, 0)
+            v = ops.sdf_mlp_forward(xc, self.packed, self.pe_w, self.mode, want_feat=False)[0][:, 0]   # same weights and
+            # precision mode as the march (not sdf_net.mlp_mode)
             return xo, xc, torch.where(ok, v, torch.full_like(v, 1e10))
         t = t0 + (t1 - t0) * s0 / (s0 - s1)
         xo, xc, v = eval_at(t)
