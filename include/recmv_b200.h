@@ -144,6 +144,44 @@ RECMV_API int recmv_sdf_pack_weights(const float* W_all, const float* b_all, voi
 RECMV_API int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float* pe_w /*host*/,
                       float* out_sdf, float* out_feat, int64_t P, int mode, recmv_stream_t stream);
 
+/* ---- A2/A3 training path: what `loss.backward()` (train.py:325) runs through model/network.py:89-119 ---------
+ * (and through Deformer.py:171-206 / RenderNet.py:59-96 -- the entry points below are generic over the layer list).
+ *
+ * recmv_sdf_mlp_fwd_train: recmv_sdf_mlp_fwd + every layer's INPUT saved in fp32 for the backward: act[l] (host array
+ *   of 9 device pointers) = [P][act_ld[l]] input of layer l; act[0] = PE(x) (39 columns used), act[l] = softplus
+ *   output of layer l-1, act[4] = [a_3 (473) | PE (39)] -- the skip concatenation WITHOUT its 1/sqrt2 (that factor
+ *   is part of the packed layer-4 weights).  act_ld[l] >= layer input width, multiple of 4.  TC modes only.
+ *
+ * recmv_mlp_bwd_data_layer: G_prev = (G . W) * act'(saved_input)  for ONE layer, on tcgen05 (3 fp16 MMAs per product):
+ *   G [P][ldg] cotangent of the layer output (out_dim columns used), W [out_dim][in_dim] row-major fp32 (the
+ *   nn.Linear layout -- no transposed copy), saved_input [P][lds] = the layer's input as saved by the forward
+ *   (= the previous layer's activation output), act: 0 none, 1 softplus(beta 100) -> 1 - exp(-100 a), 2 ReLU -> a > 0.
+ *   Columns n < split go to G_prev[p * ldgp + n] with the activation derivative; columns n >= split (the PE part
+ *   of the SDF skip layer; split <= 0 = none) go to D2[p * ldd2 + n - split] untouched.  out_scale multiplies
+ *   everything (1/sqrt2 for the SDF skip layer).  dyn_scale: optional DEVICE scalar, a power of two that brings
+ *   max|G| near 1 before the fp16 split (gradients of mean-reduced losses are ~1/P); results are unscaled again.
+ *
+ * recmv_mlp_bwd_weight: for every layer l < num_layers in ONE launch:  dW[l] [out][in] = out_scale[l] * G[l]^T X[l]
+ *   (reduction over the P samples, accumulated in chunks of 2048 samples; tile owner adds chunks in fp32 -- no atomics,
+ *   deterministic) and db[l] [out] += column sums of G[l] (db must be zero-filled by the caller; may be NULL).
+ *   G, ldg, X, ldx, out_dim, in_dim, dW, db, out_scale are HOST arrays of length num_layers (<= 10).
+ *
+ * recmv_pe_backward: dx [P,3] (+)= (d PE / d x)^T (g + g2): g [P][ldg] cotangent of the 3 + 6*bands encoding
+ *   (model/Embedder.py:43-50 order), g2 optional second cotangent of the same encoding, pe_w [2*bands] host.       */
+RECMV_API int recmv_sdf_mlp_fwd_train(const float* x, const void* packed, const float* pe_w /*host*/, float* out_sdf,
+                            float* out_feat, float* const* act /*host[9]*/, const int* act_ld /*host[9]*/,
+                            int64_t P, int mode, recmv_stream_t stream);
+RECMV_API int recmv_mlp_bwd_data_layer(const float* G, int64_t ldg, const float* W, int out_dim, int in_dim,
+                             const float* saved_input, int64_t lds, int act, int split, float* G_prev, int64_t ldgp,
+                             float* D2, int64_t ldd2, float out_scale, const float* dyn_scale /*device*/, int64_t P,
+                             recmv_stream_t stream);
+RECMV_API int recmv_mlp_bwd_weight(int num_layers, const float* const* G, const int64_t* ldg, const float* const* X,
+                         const int64_t* ldx, const int* out_dim, const int* in_dim, float* const* dW, float* const* db,
+                         const float* out_scale, const float* dyn_scale /*device*/, int64_t P, recmv_stream_t stream);
+RECMV_API int recmv_pe_backward(const float* x, const float* g, int64_t ldg, const float* g2, int64_t ldg2,
+                      const float* pe_w /*host*/, int bands, float* dx, int accumulate, int64_t P,
+                      recmv_stream_t stream);
+
 /* ---- A3: sdf and its input gradient (ImplicitNetwork.gradient, model/network.py:121-133; the
  * autograd.grad(sdf, p) of utils/FindSurfacePs.py:176 and OptimGarmentNetwork.py:1171,3192) --------------
  * One forward-mode launch of the tcgen05 kernel: every point occupies four tile rows (value and the three

@@ -63,6 +63,15 @@ SIGNATURES = {
                                   c_int, c_void_p]),
     "recmv_sdf_mlp_fwd_grad": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_void_p, c_int64,
                                        c_int, c_void_p]),
+    "recmv_sdf_mlp_fwd_train": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, POINTER(c_void_p),
+                                        POINTER(c_int), c_int64, c_int, c_void_p]),
+    "recmv_mlp_bwd_data_layer": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_int,
+                                         c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p, c_int64, c_void_p]),
+    "recmv_mlp_bwd_weight": (c_int, [c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p), POINTER(c_int64),
+                                     POINTER(c_int), POINTER(c_int), POINTER(c_void_p), POINTER(c_void_p),
+                                     POINTER(c_float), c_void_p, c_int64, c_void_p]),
+    "recmv_pe_backward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, POINTER(c_float), c_int, c_void_p,
+                                  c_int, c_int64, c_void_p]),
     "recmv_translator_packed_bytes": (c_size_t, []),
     "recmv_translator_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "recmv_deformer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, POINTER(c_float),

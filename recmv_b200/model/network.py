@@ -57,6 +57,7 @@ class ImplicitNetwork(nn.Module):
         self.softplus = nn.Softplus(beta=100)
         self.rendcond = None
         self.mlp_mode = None  # None -> ops.DEFAULT_MLP_MODE
+        self.train_fused = True   # grad-enabled forwards go through ops.SdfMlpTrainFunction (False: torch graph)
         self.last_path = None
         self._packed = None
         self._packed_key = None
@@ -103,6 +104,17 @@ class ImplicitNetwork(nn.Module):
             return sdf
         if not input.is_cuda:
             raise RuntimeError("recmv_b200.ImplicitNetwork runs on CUDA tensors only (no CPU path)")
+        mode = ops.DEFAULT_MLP_MODE if self.mlp_mode is None else self.mlp_mode
+        if self._fusable and self.train_fused and mode != ops.MLP_FP32_SIMT and input.dim() == 2:
+            # training path: fused forward that saves the layer inputs + tcgen05 backward (ops.SdfMlpTrainFunction);
+            # weight-norm's W = g v / |v| stays a (tiny) torch graph so (g, v) receive their gradients from dW
+            self.last_path = "fused-train"
+            Ws, bs = self.effective_weights()
+            sdf, feat = ops.SdfMlpTrainFunction.apply(input.contiguous().float(), self._pe_weights(ratio), mode,
+                                                      self.packed_weights(),
+                                                      *Ws, *bs)
+            self.rendcond = feat
+            return sdf
         self.last_path = "autograd-composite"
         return self._forward_graph(input, ratio)
 

@@ -382,6 +382,172 @@ def sdf_value_and_grad(x, packed, pe_w=None, mode=None, want_feat=False):
     return sdf, grad, feat
 
 
+# --------------------------------------------------------------------------------------------------
+# Training path: fused forward that saves the layer inputs + tcgen05 backward GEMMs (csrc/gemm3.cu)
+# --------------------------------------------------------------------------------------------------
+ACT_NONE, ACT_SOFTPLUS100, ACT_RELU = 0, 1, 2
+_INV_SQRT2 = 0.70710678118654752440
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
+
+
+def grad_dyn_scale(*cotangents):
+    """Device scalar 2^-floor(log2(max|g|)) (1 for an all-zero cotangent): brings the largest cotangent entry into
+    [1, 2) before the fp16 hi/lo split of the backward GEMMs; no host synchronisation."""
+    m = torch.stack([c.detach().abs().amax() for c in cotangents if c is not None]).amax().float()
+    e = torch.floor(torch.log2(m.clamp_min(1e-30)))
+    s = torch.exp2(-e.clamp(-100.0, 100.0))
+    return torch.where(m > 0, s, torch.ones_like(s)).reshape(1).contiguous()
+
+
+def mlp_bwd_data_layer(G, W, out_dim, in_dim, saved_input, act, G_prev, split=0, D2=None, out_scale=1.0, dyn_scale=None):
+    """G_prev[:, :split] = ((G[:, :out_dim] @ W) * out_scale)[:, :split] * act'(saved_input); columns >= split -> D2."""
+    P = G.shape[0]
+    with torch.cuda.device(G.device):
+        check(_lib.load().recmv_mlp_bwd_data_layer(
+            _ptr(G), G.stride(0), _ptr(W), int(out_dim), int(in_dim), _ptr(saved_input),
+            saved_input.stride(0) if saved_input is not None else 0, int(act), int(split), _ptr(G_prev), G_prev.stride(0),
+            _ptr(D2), D2.stride(0) if D2 is not None else 0, float(out_scale), _ptr(dyn_scale), P, _stream(G)),
+            "recmv_mlp_bwd_data_layer")
+    return G_prev
+
+
+def mlp_bwd_weight(Gs, Xs, out_dims, in_dims, out_scales=None, dyn_scale=None, want_bias=True):
+    """dW[l] = out_scale[l] * Gs[l][:, :out]^T @ Xs[l][:, :in] and db[l] = Gs[l][:, :out].sum(0), all layers in one launch."""
+    n = len(Gs)
+    dev = Gs[0].device
+    P = Gs[0].shape[0]
+    dW = [torch.empty((o, i), dtype=torch.float32, device=dev) for o, i in zip(out_dims, in_dims)]
+    db = [torch.zeros((o,), dtype=torch.float32, device=dev) for o in out_dims] if want_bias else None
+    scales = (c_float * n)(*[float(v) for v in (out_scales or [1.0] * n)])
+    with torch.cuda.device(dev):
+        check(_lib.load().recmv_mlp_bwd_weight(
+            n, _ptr_array(Gs), (c_int64 * n)(*[g.stride(0) for g in Gs]), _ptr_array(Xs),
+            (c_int64 * n)(*[x.stride(0) for x in Xs]), (ctypes.c_int * n)(*out_dims), (ctypes.c_int * n)(*in_dims),
+            _ptr_array(dW), _ptr_array(db) if db is not None else None, scales, _ptr(dyn_scale), P, _stream(Gs[0])),
+            "recmv_mlp_bwd_weight")
+    return dW, db
+
+
+def pe_backward(x, g, g2, pe_w, bands, dx=None):
+    """dx (+)= (d PE/d x)^T (g + g2); g / g2 [P, >= 3 + 6 bands] (row stride free), x [P,3]."""
+    P = x.shape[0]
+    acc = dx is not None
+    if dx is None:
+        dx = torch.empty((P, 3), dtype=torch.float32, device=x.device)
+    w = (c_float * (2 * bands))(*[float(v) for v in pe_w[:2 * bands]])
+    with torch.cuda.device(x.device):
+        check(_lib.load().recmv_pe_backward(_ptr(x), _ptr(g), g.stride(0), _ptr(g2), g2.stride(0) if g2 is not None else 0,
+                                            w, int(bands), _ptr(dx), 1 if acc else 0, P, _stream(x)), "recmv_pe_backward")
+    return dx
+
+
+def _pe_torch(x, pe_w, bands):
+    outs, f = [x], 1.0
+    for k in range(bands):
+        outs += [pe_w[2 * k] * torch.sin(x * f), pe_w[2 * k + 1] * torch.cos(x * f)]
+        f *= 2.0
+    return torch.cat(outs, -1)
+
+
+def _sdf_composite(x, Ws, bs, pe_w):
+    """The same network as a torch graph (model/network.py:89-119) -- the twice-differentiable fallback of the
+    training Function's backward when the caller asked for create_graph=True."""
+    pe = _pe_torch(x, pe_w, 6)
+    h = pe
+    for l in range(9):
+        if l == 4:
+            h = torch.cat([h, pe], 1) * _INV_SQRT2
+        h = torch.nn.functional.linear(h, Ws[l], bs[l])
+        if l < 8:
+            h = torch.nn.functional.softplus(h, beta=100)
+    return h[:, :1], h[:, 1:]
+
+
+class SdfMlpTrainFunction(torch.autograd.Function):
+    """ImplicitNetwork.forward with gradients (model/network.py:89-119 inside train.py:317-330).
+
+    forward : ONE fused tcgen05 launch (PE + 9 linears + softplus, activations on-chip) that also writes every layer's
+              input to HBM in fp32 (recmv_sdf_mlp_fwd_train) -- 16 KB per point, what autograd would keep anyway.
+    backward: first order (`loss.backward()`, parameter VJPs of propagateTmpPsGrad) -> 9 backward-data launches +
+              ONE weight-gradient launch + the PE Jacobian, all on tcgen05 in the engine's fp32-grade arithmetic
+              (csrc/gemm3.cu); weight-norm's (g, v) and anything upstream of x stay ordinary autograd.
+              Called with create_graph=True (eikonal / normals, network.py:121-133) the backward instead re-runs the
+              network as a torch graph over the saved inputs -- twice differentiable, on cuBLAS; `last_backward` says
+              which ran."""
+    last_backward = None
+
+    @staticmethod
+    def forward(ctx, x, pe_w, mode, packed, *Wb):
+        Ws, bs = Wb[:9], Wb[9:]
+        if not (x.is_contiguous() and x.dtype == torch.float32 and x.dim() == 2):
+            raise RuntimeError("SdfMlpTrainFunction expects a contiguous float32 [P,3] tensor (convert outside, in the graph)")
+        P = x.shape[0]
+        dev = x.device
+        act = [torch.empty((P, 64), dtype=torch.float32, device=dev)] + \
+              [torch.empty((P, 512), dtype=torch.float32, device=dev) for _ in range(8)]
+        sdf = torch.empty((P, 1), dtype=torch.float32, device=dev)
+        feat = torch.empty((P, 256), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.load().recmv_sdf_mlp_fwd_train(_ptr(x), _ptr(packed), _pe_array(pe_w), _ptr(sdf), _ptr(feat),
+                                                      _ptr_array(act), (ctypes.c_int * 9)(*[a.stride(0) for a in act]),
+                                                      P, mode, _stream(x)), "recmv_sdf_mlp_fwd_train")
+        ctx.pe_w, ctx.mode = [float(w) for w in pe_w], mode
+        ctx.save_for_backward(x, *Ws, *bs, *act)
+        return sdf, feat
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_feat):
+        saved = ctx.saved_tensors
+        x, Ws, bs, act = saved[0], saved[1:10], saved[10:19], saved[19:28]
+        P = x.shape[0]
+        dev = x.device
+        need_x = ctx.needs_input_grad[0]
+        need_w = any(ctx.needs_input_grad[4:])
+        if torch.is_grad_enabled():
+            # create_graph=True: differentiate a torch graph of the same network (second order stays on torch)
+            SdfMlpTrainFunction.last_backward = "autograd-composite (create_graph)"
+            xi = x if x.requires_grad else x.detach().requires_grad_(need_x)
+            with torch.enable_grad():
+                sdf, feat = _sdf_composite(xi, Ws, bs, ctx.pe_w)
+                ins = [t for t in [xi] + list(Ws) + list(bs) if t.requires_grad]
+                outs, gos = [sdf], [g_sdf if g_sdf is not None else torch.zeros_like(sdf)]
+                if g_feat is not None:
+                    outs.append(feat); gos.append(g_feat)
+                gr = torch.autograd.grad(outs, ins, gos, create_graph=True, allow_unused=True)
+            it = iter(gr)
+            res = [next(it) if t.requires_grad else None for t in [xi] + list(Ws) + list(bs)]
+            return (res[0] if need_x else None, None, None, None, *res[1:])
+        SdfMlpTrainFunction.last_backward = "fused-tcgen05"
+        G8 = torch.zeros((P, 260), dtype=torch.float32, device=dev)
+        if g_sdf is not None:
+            G8[:, 0:1] = g_sdf
+        if g_feat is not None:
+            G8[:, 1:257] = g_feat
+        dyn = grad_dyn_scale(G8)
+        G = [None] * 9
+        G[8] = G8
+        dpe4 = torch.empty((P, 40), dtype=torch.float32, device=dev)
+        outs = [w.shape[0] for w in Ws]
+        ins = [w.shape[1] for w in Ws]
+        for l in range(8, 0, -1):
+            G[l - 1] = torch.empty((P, 512), dtype=torch.float32, device=dev)
+            mlp_bwd_data_layer(G[l], Ws[l], outs[l], ins[l], act[l], ACT_SOFTPLUS100, G[l - 1],
+                               split=473 if l == 4 else 0, D2=dpe4 if l == 4 else None,
+                               out_scale=_INV_SQRT2 if l == 4 else 1.0, dyn_scale=dyn)
+        dx = None
+        if need_x:
+            dpe0 = torch.empty((P, 40), dtype=torch.float32, device=dev)
+            mlp_bwd_data_layer(G[0], Ws[0], outs[0], ins[0], None, ACT_NONE, dpe0, dyn_scale=dyn)
+            dx = pe_backward(x, dpe0, dpe4, ctx.pe_w, 6)
+        dW, db = [None] * 9, [None] * 9
+        if need_w:
+            dW, db = mlp_bwd_weight(G, list(act), outs, ins, [_INV_SQRT2 if l == 4 else 1.0 for l in range(9)], dyn)
+        return (dx, None, None, None, *dW, *db)
+
+
 TRANSLATOR_LAYER_SHAPES = [(512, 167), (512, 512), (512, 512), (512, 512), (3, 512)]
 
 

@@ -1,0 +1,137 @@
+"""GPU parity of the TRAINING path of the SDF network: the fused forward that saves the layer inputs and the tcgen05
+backward GEMMs (csrc/gemm3.cu) behind `loss.backward()`, against
+  * the gradients torch autograd produces through the REFERENCE's own ImplicitNetwork (fp32 = the reference's numbers,
+    fp64 = ground truth), tests/golden/sdf_bwd_*.npz from tests/golden/make_golden_r2.py;
+  * fp64 matmuls for the two GEMM entry points at ragged shapes.
+Metric: max |a - b| / max |b| per tensor (a gradient tensor's entries span decades; its scale is its largest entry).
+Bound 1e-4 against the fp64 truth (the reference's own fp32 autograd sits 2e-7 .. 2e-6 from it)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from recmv_b200 import _lib, ops, synth, testing
+from recmv_b200.model import getTmpSdf
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def _no_aborted_launch():
+    yield
+    torch.cuda.synchronize()
+    ops.check_async_errors()
+
+
+def cotangents(P, nfeat, seed):      # tests/golden/make_golden_r2.py
+    g = synth.generator(seed)
+    mag = torch.exp(torch.randn((P, 1), generator=g) * 1.0) / P
+    c0 = torch.randn((P, 1), generator=g) * mag
+    c1 = torch.randn((P, nfeat), generator=g) * mag * 0.1
+    return c0, c1
+
+
+def merr(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).detach().cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).detach().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+@pytest.mark.parametrize("P,out_dim,in_dim,act,split", [(1, 512, 512, 1, 0), (300, 257, 512, 1, 0), (1000, 512, 512, 1, 473),
+                                                          (129, 473, 512, 2, 0), (777, 512, 39, 0, 0), (4096, 3, 512, 2, 0)])
+def test_bwd_data_layer_matches_fp64(P, out_dim, in_dim, act, split):
+    g = synth.generator(P + out_dim)
+    G = (torch.randn((P, 512), generator=g) * 1e-4).to(DEV)
+    W = (torch.randn((out_dim, in_dim), generator=g) * 0.05).to(DEV)
+    X = torch.nn.functional.softplus(torch.randn((P, 512), generator=g) * 0.02, beta=100).to(DEV)
+    if act == 2:
+        X = torch.relu(torch.randn((P, 512), generator=g)).to(DEV)
+    dyn = ops.grad_dyn_scale(G[:, :out_dim])
+    out = torch.full((P, 512), 7.0, device=DEV)
+    d2 = torch.full((P, 40), 7.0, device=DEV) if split else None
+    ops.mlp_bwd_data_layer(G, W, out_dim, in_dim, X if act else None, act, out, split=split, D2=d2, out_scale=0.5,
+                           dyn_scale=dyn)
+    ref = (G[:, :out_dim].double() @ W.double()) * 0.5
+    xs = X[:, :in_dim].double()
+    deriv = {0: torch.ones_like(xs), 1: 1 - torch.exp(-100 * xs), 2: (xs > 0).double()}[act]
+    n_act = split if split else in_dim
+    assert merr(out[:, :n_act], ref[:, :n_act] * deriv[:, :n_act]) < 2e-6
+    if split:
+        assert merr(d2[:, :in_dim - split], ref[:, split:]) < 2e-6
+        assert bool((d2[:, in_dim - split:] == 7.0).all())
+    assert bool((out[:, in_dim if not split else split:] == 7.0).all())      # nothing written outside the layer width
+
+
+@pytest.mark.parametrize("P", [1, 63, 2048, 5000])
+def test_bwd_weight_matches_fp64(P):
+    g = synth.generator(P)
+    dims = [(512, 39, 64), (473, 512, 512), (257, 512, 512), (3, 167, 192)]
+    Gs = [(torch.randn((P, 512), generator=g) * 1e-3).to(DEV) for _ in dims]
+    Xs = [torch.rand((P, ld), generator=g).to(DEV) for (_, _, ld) in dims]
+    dyn = ops.grad_dyn_scale(*Gs)
+    dW, db = ops.mlp_bwd_weight(Gs, Xs, [d[0] for d in dims], [d[1] for d in dims], [1.0, 0.5, 1.0, 1.0], dyn)
+    dW2, _ = ops.mlp_bwd_weight(Gs, Xs, [d[0] for d in dims], [d[1] for d in dims], [1.0, 0.5, 1.0, 1.0], dyn, want_bias=False)
+    for (o, i, _), Gl, Xl, w, b, sc, w2 in zip(dims, Gs, Xs, dW, db, [1.0, 0.5, 1.0, 1.0], dW2):
+        ref = (Gl[:, :o].double().t() @ Xl[:, :i].double()) * sc
+        assert w.shape == (o, i) and merr(w, ref) < 3e-6
+        assert merr(b, Gl[:, :o].double().sum(0)) < 3e-6
+        assert torch.equal(w, w2)                                     # deterministic (no atomics on dW)
+
+
+@pytest.mark.parametrize("tag", ["geo", "trained"])
+def test_loss_backward_matches_reference_autograd(tag):
+    g = load_golden(f"sdf_bwd_{tag}.npz")
+    x0 = torch.from_numpy(load_golden(f"sdf_c1_{tag}.npz")["x"])[:2048]
+    net = testing.build_sdf(getTmpSdf, seed=0, perturb_seed=None if tag == "geo" else 101).to(DEV)
+    c0, c1 = cotangents(2048, 256, 77)
+    x = x0.to(DEV).requires_grad_(True)
+    y = net(x, {'sdfRatio': 0.7})
+    assert net.last_path == "fused-train"
+    loss = (y * c0.to(DEV)).sum() + (net.rendcond * c1.to(DEV)).sum()
+    loss.backward()
+    assert ops.SdfMlpTrainFunction.last_backward == "fused-tcgen05"
+    rows = [("dx", merr(x.grad, g["dx_f64"]), merr(g["dx_f32"], g["dx_f64"]))]
+    for l in range(9):
+        lin = getattr(net, f"lin{l}")
+        rows.append((f"lin{l}.bias", merr(lin.bias.grad, g[f"f64_lin{l}_bias"]), merr(g[f"f32_lin{l}_bias"], g[f"f64_lin{l}_bias"])))
+        rows.append((f"lin{l}.weight_g", merr(lin.weight_g.grad, g[f"f64_lin{l}_weight_g"]),
+                     merr(g[f"f32_lin{l}_weight_g"], g[f"f64_lin{l}_weight_g"])))
+        gv = lin.weight_v.grad
+        if f"f64_lin{l}_weight_v_sample" in g:
+            for part, ours in (("sample", gv[::16, ::8]), ("rowsum", gv.double().sum(1)), ("colsum", gv.double().sum(0))):
+                k = f"lin{l}_weight_v_{part}"
+                scale = float(g[f"f64_lin{l}_weight_v_absmax"]) * (1 if part == "sample" else 16)
+                e = float((torch.as_tensor(ours).double().cpu() - torch.from_numpy(g["f64_" + k]).double()).abs().max()) / scale
+                e_ref = float(np.abs(g["f32_" + k].astype(np.float64) - g["f64_" + k]).max()) / scale
+                rows.append((k, e, e_ref))
+        else:
+            rows.append((f"lin{l}.weight_v", merr(gv, g[f"f64_lin{l}_weight_v"]), merr(g[f"f32_lin{l}_weight_v"], g[f"f64_lin{l}_weight_v"])))
+    table = "\n".join(f"{tag}/{n}: |ours-f64| {a:.2e}  |ref32-f64| {b:.2e}" for n, a, b in rows)
+    print(table)
+    for n, a, b in rows:
+        assert a < 1e-4, table
+
+
+def test_create_graph_goes_through_the_torch_graph_and_matches():
+    """gradient(x) with create_graph=True (network.py:121-133; eikonal term) re-runs the network as a torch graph inside
+    the Function's backward: second-order gradients exist and agree with the all-torch module."""
+    net = testing.build_sdf(getTmpSdf, seed=0, perturb_seed=101).to(DEV)
+    x0 = (torch.rand((512, 3), generator=synth.generator(5)) * 1.2 - 0.6).to(DEV)
+
+    def eikonal(fused):
+        net.train_fused = fused
+        net.zero_grad()
+        x = x0.clone().requires_grad_(True)
+        gr = net.gradient(x)
+        loss = ((gr.norm(dim=1) - 1) ** 2).mean()
+        loss.backward()
+        return gr.detach(), [p.grad.clone() for p in net.parameters()], x.grad.clone()
+    g1, p1, x1 = eikonal(True)
+    assert net.last_path == "fused-train" and "create_graph" in ops.SdfMlpTrainFunction.last_backward
+    g2, p2, x2 = eikonal(False)
+    assert net.last_path == "autograd-composite"
+    assert merr(g1, g2) < 1e-4 and merr(x1, x2) < 2e-3
+    for a, b in zip(p1, p2):
+        assert merr(a, b) < 2e-3
+    net.train_fused = True
