@@ -90,11 +90,15 @@ def test_sdf_c1_matches_reference_golden(name, mode, ntol, tol, tag):
         with torch.no_grad():
             y = net(x[:P], {"sdfRatio": None})
         assert rel_err(y[:, 0], g["sdf_none"][:P], 1e-2) < tol
-    # input gradient through the autograd-composite graph equals the reference's
+    # input gradient through autograd equals the reference's: the tcgen05 training path (fused forward that saves the
+    # layer inputs + backward GEMMs) for the tc modes, the torch graph for the fp32 SIMT mode
     xg = x.clone().requires_grad_(True)
     gr = torch.autograd.grad(net(xg, None).sum(), xg)[0]
-    assert net.last_path == "autograd-composite"
-    assert rel_err(gr, g["grad_none"], 1e-2) < 1e-4
+    assert net.last_path == ("autograd-composite" if mode == _lib.MLP_FP32_SIMT else "fused-train")
+    if mode == _lib.MLP_FP32_SIMT:
+        assert rel_err(gr, g["grad_none"], 1e-2) < 1e-4
+    else:   # backward GEMMs: error relative to the gradient's scale (tests/test_gpu_train.py holds the full comparison)
+        assert norm_err(gr, g["grad_none"]) < (3e-5 if name != "tc1" else 2e-2)
 
 
 @pytest.mark.parametrize("name,mode", [("simt", _lib.MLP_FP32_SIMT), ("tc3", _lib.MLP_TC_F16X3)])

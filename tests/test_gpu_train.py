@@ -4,7 +4,7 @@ backward GEMMs (csrc/gemm3.cu) behind `loss.backward()`, against
     fp64 = ground truth), tests/golden/sdf_bwd_*.npz from tests/golden/make_golden_r2.py;
   * fp64 matmuls for the two GEMM entry points at ragged shapes.
 Metric: max |a - b| / max |b| per tensor (a gradient tensor's entries span decades; its scale is its largest entry).
-Bound 1e-4 against the fp64 truth (the reference's own fp32 autograd sits 2e-7 .. 2e-6 from it)."""
+Bound 3e-5 against the fp64 truth (the reference's own fp32 autograd sits 2e-7 .. 9e-6 from it in the same metric)."""
 import numpy as np
 import pytest
 import torch
@@ -56,9 +56,9 @@ def test_bwd_data_layer_matches_fp64(P, out_dim, in_dim, act, split):
     xs = X[:, :in_dim].double()
     deriv = {0: torch.ones_like(xs), 1: 1 - torch.exp(-100 * xs), 2: (xs > 0).double()}[act]
     n_act = split if split else in_dim
-    assert merr(out[:, :n_act], ref[:, :n_act] * deriv[:, :n_act]) < 2e-6
+    assert merr(out[:, :n_act], ref[:, :n_act] * deriv[:, :n_act]) < 1.5e-6
     if split:
-        assert merr(d2[:, :in_dim - split], ref[:, split:]) < 2e-6
+        assert merr(d2[:, :in_dim - split], ref[:, split:]) < 1.5e-6
         assert bool((d2[:, in_dim - split:] == 7.0).all())
     assert bool((out[:, in_dim if not split else split:] == 7.0).all())      # nothing written outside the layer width
 
@@ -74,7 +74,7 @@ def test_bwd_weight_matches_fp64(P):
     dW2, _ = ops.mlp_bwd_weight(Gs, Xs, [d[0] for d in dims], [d[1] for d in dims], [1.0, 0.5, 1.0, 1.0], dyn, want_bias=False)
     for (o, i, _), Gl, Xl, w, b, sc, w2 in zip(dims, Gs, Xs, dW, db, [1.0, 0.5, 1.0, 1.0], dW2):
         ref = (Gl[:, :o].double().t() @ Xl[:, :i].double()) * sc
-        assert w.shape == (o, i) and merr(w, ref) < 3e-6
+        assert w.shape == (o, i) and merr(w, ref) < 2e-6
         assert merr(b, Gl[:, :o].double().sum(0)) < 3e-6
         assert torch.equal(w, w2)                                     # deterministic (no atomics on dW)
 
@@ -110,7 +110,7 @@ def test_loss_backward_matches_reference_autograd(tag):
     table = "\n".join(f"{tag}/{n}: |ours-f64| {a:.2e}  |ref32-f64| {b:.2e}" for n, a, b in rows)
     print(table)
     for n, a, b in rows:
-        assert a < 1e-4, table
+        assert a < 3e-5, table
 
 
 def test_create_graph_goes_through_the_torch_graph_and_matches():
