@@ -242,7 +242,44 @@ def secondary_rates(dev, ren, mode):
         return {"points_per_s": P / (ms * 1e-3), "ms_per_1M_points": ms,
                 "algorithmic_tflops": flop_per_point * P / (ms * 1e-3) / 1e12}
 
+    # training step of the SDF network on the same engine: fused forward that saves the layer inputs + tcgen05 backward
+    # GEMMs (backward-data per layer, ONE weight-gradient launch) behind loss.backward(); ALGORITHMIC FLOP per point =
+    # 3 x 3 933 184 (forward, backward-data, weight gradient), each issued as 3 fp16 MMAs per product
+    Pt = 1 << 17
+    xt = pts[:Pt].clone()
+    c_sdf = (torch.randn((Pt, 1), generator=g) / Pt).to(dev)
+    c_feat = (torch.randn((Pt, 256), generator=g) / Pt * 0.1).to(dev)
+
+    def train_step():
+        for p_ in sdf_net.parameters():
+            p_.grad = None
+        xg = xt.detach().requires_grad_(True)
+        y = sdf_net(xg, None)
+        ((y * c_sdf).sum() + (sdf_net.rendcond * c_feat).sum()).backward()
+
+    def rate_train():
+        for _ in range(2):
+            train_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            train_step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 5
+        tf = 3 * FLOP_PER_SAMPLE * Pt / (ms * 1e-3) / 1e12
+        peaks, _ = measured_peaks()
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        return {"points_per_s": Pt / (ms * 1e-3), "ms_per_step": ms, "points": Pt, "path": sdf_net.last_path,
+                "backward": ops.SdfMlpTrainFunction.last_backward, "algorithmic_tflops": tf,
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                             "mma_passes": 3, "issued_frac": 3 * tf / peak_tf},
+                "includes": "weight-norm graph, cotangent packing, 9 backward-data launches, 1 weight-gradient launch, "
+                            "PE Jacobian, autograd bookkeeping (everything loss.backward() runs)"}
+    train = rate_train()
+
     return {
+        "sdf_train_step (fused forward + tcgen05 backward, loss.backward())": train,
         "deformer_fwd (MLPTranslator + LBS, one launch)": rate(
             lambda: deformer(pts, [conds, [poses, trans]], bi, ratio=ratio, offset_type="body"), 1746944),
         "deformer_fwd_jac (value + 3x3 Jacobian, forward mode)": rate(

@@ -43,8 +43,22 @@ def _worker(rank, world, port, q):
     b0, bn = shard_rows(64, rank, world)
     (net(x[b0:b0 + bn]).sum() / 64.0).backward()
     allreduce_grads(list(net.parameters()), comm_stream=torch.cuda.Stream(dev)).wait()
+    # (3) the real thing: data-parallel training step of the SDF network (fused forward + tcgen05 backward), each rank on
+    # its shard of the points, loss normalised by the GLOBAL point count, one flat all-reduce of all parameter gradients
+    from recmv_b200 import ops, testing
+    from recmv_b200.model import getTmpSdf
+    sdfnet = testing.build_sdf(getTmpSdf, seed=0, perturb_seed=101).to(dev)
+    P = 1024
+    xs = (torch.rand((P, 3), generator=torch.Generator().manual_seed(9)) * 1.2 - 0.6).to(dev)
+    s0, sn = shard_rows(P, rank, world)
+    y = sdfnet(xs[s0:s0 + sn].clone().requires_grad_(False), 0.7)
+    ((y.pow(2).sum() + sdfnet.rendcond.pow(2).sum() * 0.01) / P).backward()
+    assert sdfnet.last_path == "fused-train" and ops.SdfMlpTrainFunction.last_backward == "fused-tcgen05"
+    allreduce_grads(list(sdfnet.parameters()), comm_stream=torch.cuda.Stream(dev)).wait()
     torch.cuda.synchronize(dev)
-    q.put((rank, r0, sdf.cpu().numpy(), hit_idx.cpu().numpy(), [p.grad.cpu().numpy() for p in net.parameters()]))
+    ops.check_async_errors()
+    q.put((rank, r0, sdf.cpu().numpy(), hit_idx.cpu().numpy(), [p.grad.cpu().numpy() for p in net.parameters()],
+           [p.grad.cpu().numpy() for p in sdfnet.parameters()]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,3 +91,17 @@ def test_two_gpu_sharded_render_and_grad_allreduce():
     for g in got:
         for a, p in zip(g[4], net.parameters()):
             assert torch.allclose(torch.from_numpy(a).to(dev), p.grad, atol=1e-6)
+    # data-parallel SDF training step == the single-GPU full-batch step (up to the summation order of the all-reduce)
+    from recmv_b200 import testing
+    from recmv_b200.model import getTmpSdf
+    sdfnet = testing.build_sdf(getTmpSdf, seed=0, perturb_seed=101).to(dev)
+    P = 1024
+    xs = (torch.rand((P, 3), generator=torch.Generator().manual_seed(9)) * 1.2 - 0.6).to(dev)
+    y = sdfnet(xs, 0.7)
+    ((y.pow(2).sum() + sdfnet.rendcond.pow(2).sum() * 0.01) / P).backward()
+    for g in got:
+        for a, p in zip(g[5], sdfnet.parameters()):
+            a = torch.from_numpy(a).to(dev)
+            assert float((a - p.grad).abs().max()) <= 2e-5 * float(p.grad.abs().max()) + 1e-12
+        for a, b in zip(g[5], got[0][5]):
+            assert np.array_equal(a, b)                     # every rank holds the same reduced gradients
