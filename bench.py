@@ -208,6 +208,7 @@ def secondary_rates(dev, ren, mode):
     network.  ALGORITHMIC FLOP per point: SURVEY 8d (translator 1 746 944, colour net 1 871 872, SDF 3 933 184;
     the forward-mode launches carry 4 rows per point)."""
     import recmv_b200.model as M
+    from recmv_b200 import ops
     from recmv_b200 import synth as sy
     P = 1 << 20
     g = sy.generator(21)
@@ -461,7 +462,7 @@ def main():
         mc_bytes = 4 * 257 ** 3 + 12 * v.shape[0] + 24 * f.shape[0]   # SURVEY 8d algorithmic bytes
         mc = {"cells_per_s": 256 ** 3 / (mc_ms * 1e-3), "ms_per_call": mc_ms, "grid": "257^3", "verts": int(v.shape[0]),
               "faces": int(f.shape[0]), "algorithmic_bytes": mc_bytes,
-              "note": "classify + count + scan + emit, end to end per call (device-resident counts)"}
+              "note": "sign mask + count + scan + vertex + face passes queued by one call, one host sync at the end, fresh output tensors"}
 
     # ---- the other networks of the path on the same engine (reported next to the headline, not part of it) -----------
     secondary = None

@@ -96,6 +96,13 @@ RECMV_API int recmv_mc_count(const float* sdf, int NX, int NY, int NZ, float iso
 RECMV_API int recmv_mc_emit(const float* sdf, int NX, int NY, int NZ, float iso, void* scratch,
                   const float step[3] /*host*/, const float origin[3] /*host*/, float* verts,
                   int64_t* faces, recmv_stream_t stream);
+/* One call, NO host synchronisation (the reference blocks on a cudaMemcpy between its two kernels,
+ * MCGpu/CudaKernels.cu:628): classify + count + scan + emit into caller-provided buffers of capacity cap_verts /
+ * cap_faces rows.  counts (DEVICE, int32[4]) receives {V, F, overflow, 0}; overflow != 0 = a buffer was too small
+ * (re-run with V / F rows).  Rows beyond V / F are left untouched.                                              */
+RECMV_API int recmv_mc_run(const float* sdf, int NX, int NY, int NZ, float iso, void* scratch,
+                 const float step[3] /*host*/, const float origin[3] /*host*/, float* verts, int64_t cap_verts,
+                 int64_t* faces, int64_t cap_faces, int32_t* counts /*device*/, recmv_stream_t stream);
 
 /* ---- A5 / A5': LBSkinner.forward and the inverse warp ----------------------------------------
  * replaces model/Deformer.py:359-445 (+342-355, GridSamplerMine3dFunction at :421).
@@ -147,10 +154,13 @@ RECMV_API int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float*
 /* ---- A2/A3 training path: what `loss.backward()` (train.py:325) runs through model/network.py:89-119 ---------
  * (and through Deformer.py:171-206 / RenderNet.py:59-96 -- the entry points below are generic over the layer list).
  *
- * recmv_sdf_mlp_fwd_train: recmv_sdf_mlp_fwd + every layer's INPUT saved in fp32 for the backward: act[l] (host array
- *   of 9 device pointers) = [P][act_ld[l]] input of layer l; act[0] = PE(x) (39 columns used), act[l] = softplus
- *   output of layer l-1, act[4] = [a_3 (473) | PE (39)] -- the skip concatenation WITHOUT its 1/sqrt2 (that factor
- *   is part of the packed layer-4 weights).  act_ld[l] >= layer input width, multiple of 4.  TC modes only.
+ * recmv_mlp_fwd_layer: Y = act(pre_scale * (X . W^T) + bias) for ONE layer on tcgen05 (3 fp16 MMAs per product, fp32
+ *   accumulation) -- the TRAINING forward, whose layer outputs stay in HBM as the inputs the backward needs (what
+ *   autograd would save): X [P][ldx] (in_dim columns used), W [out_dim][in_dim] row-major fp32 (nn.Linear layout),
+ *   bias [out_dim] or NULL, act: 0 none, 1 softplus(beta 100, threshold 20), 2 ReLU.  Columns n < split -> Y[p*ldy+n],
+ *   columns n >= split -> Y2[p*ldy2 + n - split] (split <= 0: all to Y; the SDF output layer splits sdf | features).
+ * recmv_pe_forward: positional encoding rows (model/Embedder.py:43-50 with the annealing weights pe_w [2*bands] host)
+ *   written as a saved layer input: out[p*ld + e], e < 3 + 6*bands; out2 (optional) gets the same row.
  *
  * recmv_mlp_bwd_data_layer: G_prev = (G . W) * act'(saved_input)  for ONE layer, on tcgen05 (3 fp16 MMAs per product):
  *   G [P][ldg] cotangent of the layer output (out_dim columns used), W [out_dim][in_dim] row-major fp32 (the
@@ -168,9 +178,11 @@ RECMV_API int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float*
  *
  * recmv_pe_backward: dx [P,3] (+)= (d PE / d x)^T (g + g2): g [P][ldg] cotangent of the 3 + 6*bands encoding
  *   (model/Embedder.py:43-50 order), g2 optional second cotangent of the same encoding, pe_w [2*bands] host.       */
-RECMV_API int recmv_sdf_mlp_fwd_train(const float* x, const void* packed, const float* pe_w /*host*/, float* out_sdf,
-                            float* out_feat, float* const* act /*host[9]*/, const int* act_ld /*host[9]*/,
-                            int64_t P, int mode, recmv_stream_t stream);
+RECMV_API int recmv_mlp_fwd_layer(const float* X, int64_t ldx, const float* W, const float* bias, int out_dim, int in_dim,
+                        int act, float pre_scale, int split, float* Y, int64_t ldy, float* Y2, int64_t ldy2, int64_t P,
+                        recmv_stream_t stream);
+RECMV_API int recmv_pe_forward(const float* x, const float* pe_w /*host*/, int bands, float* out, int64_t ld, float* out2,
+                     int64_t ld2, int64_t P, recmv_stream_t stream);
 RECMV_API int recmv_mlp_bwd_data_layer(const float* G, int64_t ldg, const float* W, int out_dim, int in_dim,
                              const float* saved_input, int64_t lds, int act, int split, float* G_prev, int64_t ldgp,
                              float* D2, int64_t ldd2, float out_scale, const float* dyn_scale /*device*/, int64_t P,

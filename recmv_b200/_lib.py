@@ -17,6 +17,9 @@ LAYOUT_NCDHW, LAYOUT_NDHWC = 0, 1
 MLP_FP32_SIMT, MLP_TC_F16X3, MLP_TC_F16X1 = 0, 1, 2
 
 
+RECMV_E_RANGE = -4
+
+
 class RecmvError(RuntimeError):
     pass
 
@@ -52,6 +55,8 @@ SIGNATURES = {
                                POINTER(c_int64), c_void_p]),
     "recmv_mc_emit": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, POINTER(c_float),
                               POINTER(c_float), c_void_p, c_void_p, c_void_p]),
+    "recmv_mc_run": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, POINTER(c_float), POINTER(c_float), c_void_p,
+                             c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "recmv_lbs_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                               POINTER(Voxel), c_void_p, c_void_p, c_int64, c_void_p]),
     "recmv_lbs_inverse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
@@ -63,8 +68,9 @@ SIGNATURES = {
                                   c_int, c_void_p]),
     "recmv_sdf_mlp_fwd_grad": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_void_p, c_int64,
                                        c_int, c_void_p]),
-    "recmv_sdf_mlp_fwd_train": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, POINTER(c_void_p),
-                                        POINTER(c_int), c_int64, c_int, c_void_p]),
+    "recmv_mlp_fwd_layer": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p,
+                                    c_int64, c_void_p, c_int64, c_int64, c_void_p]),
+    "recmv_pe_forward": (c_int, [c_void_p, POINTER(c_float), c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p]),
     "recmv_mlp_bwd_data_layer": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_int,
                                          c_void_p, c_int64, c_void_p, c_int64, c_float, c_void_p, c_int64, c_void_p]),
     "recmv_mlp_bwd_weight": (c_int, [c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p), POINTER(c_int64),

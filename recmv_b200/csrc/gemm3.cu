@@ -43,11 +43,13 @@ constexpr int kNumBars = 2 * kStages + 4;
 constexpr uint32_t kOffMisc = kOffBar + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffMisc + 64 + 1024 /* alignment slack */;
 
-enum { EPI_STORE = 0, EPI_SOFTPLUS100 = 1, EPI_RELU = 2, EPI_ACCUM = 3 };
+enum { EPI_STORE = 0, EPI_SOFTPLUS100 = 1, EPI_RELU = 2, EPI_ACCUM = 3,          // backward-data (0-2), weight gradient (3)
+       EPI_FWD_NONE = 4, EPI_FWD_SOFTPLUS100 = 5, EPI_FWD_RELU = 6 };                // forward layer: act(acc + bias)
 
 struct G3Task {
   const float* A; long long lda; int a_transposed;
-  const float* B; long long ldb;                    // always transposed: element (n, k) at B[k * ldb + n]
+  const float* B; long long ldb; int b_transposed;  // transposed: element (n, k) at B[k * ldb + n]; direct: B[n * ldb + k]
+  const float* bias;                                // forward layers: added after unscaling, before the activation
   float* D; long long ldd;                          // D[m * ldd + n], n < split
   float* D2; long long ldd2;                        // columns n >= split: D2[m * ldd2 + (n - split)], plain store
   const float* E; long long lde;                    // saved layer input for the activation derivative, E[m * lde + n]
@@ -217,8 +219,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
           st_shared_v4(st + kPlane + off, lo);
         }
       }
-      // ---- B tile (transposed read) ----
-      {
+      // ---- B tile ----
+      if (T.b_transposed) {
         const int r = t & 127;
         const bool rok = n0 + r < T.N;
 #pragma unroll
@@ -231,6 +233,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
             v[j] = (rok && k < T.K) ? __ldg(T.B + k * T.ldb + (n0 + r)) * sb : 0.f;
           }
           range_check8(v, prm.status, 2302);
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          const uint32_t off = sw128_offset(r, c);
+          st_shared_v4(st + 2 * kPlane + off, hi);
+          st_shared_v4(st + 3 * kPlane + off, lo);
+        }
+      } else {
+        const int c = t & 7;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (t >> 3) + 32 * i;
+          const long long k = k0 + c * 8;
+          float v[8];
+          const bool rok = n0 + r < T.N;
+          const float* src = T.B + (long long)(n0 + r) * T.ldb + k;
+          if (rok && k + 8 <= T.K && ((T.ldb & 3) == 0)) {
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(src)), x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (rok && k + j < T.K) ? __ldg(src + j) : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= sb;
+          range_check8(v, prm.status, 2303);
           uint4 hi, lo;
           split8(v, hi, lo);
           const uint32_t off = sw128_offset(r, c);
@@ -300,14 +327,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
                 }
             }
           } else {
-            // backward-data: one chunk (K = layer width); columns < split get the activation derivative
+            // backward-data / forward layer: one chunk (K = layer width).  Columns < split go to D (backward-data: times
+            // the activation derivative from the saved input E), columns >= split to D2.
+            const bool fwd = T.epi >= EPI_FWD_NONE;
 #pragma unroll 1
             for (int j4 = 0; j4 < 8; ++j4) {
               const int n = nb + 4 * j4;
               float o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(r[4 * j4 + e]) * unscale;
-              if (n + 4 <= T.split && (T.ldd & 3) == 0 && (T.E == nullptr || (T.lde & 3) == 0)) {
+              if (fwd) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (n + e >= T.N) continue;
+                  float v = o[e] + (T.bias ? __ldg(T.bias + n + e) : 0.f);
+                  if (T.epi == EPI_FWD_SOFTPLUS100) v = softplus100(v);
+                  else if (T.epi == EPI_FWD_RELU) v = fmaxf(v, 0.f);
+                  o[e] = v;
+                }
+              }
+              const bool vec = n + 4 <= T.split && (T.ldd & 3) == 0 && (fwd || T.E == nullptr || (T.lde & 3) == 0);
+              if (vec) {
                 if (T.epi == EPI_SOFTPLUS100) {
                   const float4 a = __ldg(reinterpret_cast<const float4*>(T.E + (long long)m * T.lde + n));
                   // d softplus_100(z) / dz = sigmoid(100 z) = 1 - exp(-100 a),  a = softplus_100(z)  (exact also on
@@ -406,10 +446,60 @@ __global__ void __launch_bounds__(256) pe_backward_kernel(const float* __restric
   }
   dx[i] = accumulate ? dx[i] + acc : acc;
 }
+// positional encoding written as a saved layer input: out[p * ld + e], e < 3 + 6 * bands (model/Embedder.py:43-50);
+// out2 (optional) receives the same row (the SDF network's skip input)
+__global__ void __launch_bounds__(256) pe_forward_kernel(const float* __restrict__ x, PeWeights pw, int bands,
+                                                         float* __restrict__ out, long long ld, float* __restrict__ out2,
+                                                         long long ld2, long long P) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float pe[39];
+  positional_encode(x[3 * p], x[3 * p + 1], x[3 * p + 2], pw.w, pe);
+  const int n = 3 + 6 * bands;
+  for (int e = 0; e < n; ++e) {
+    out[p * ld + e] = pe[e];
+    if (out2) out2[p * ld2 + e] = pe[e];
+  }
+}
 }  // namespace
 }  // namespace recmv
 
 using namespace recmv;
+
+extern "C" int recmv_mlp_fwd_layer(const float* X, int64_t ldx, const float* W, const float* bias, int out_dim, int in_dim,
+                                   int act, float pre_scale, int split, float* Y, int64_t ldy, float* Y2, int64_t ldy2,
+                                   int64_t P, recmv_stream_t stream) {
+  if (P < 0 || out_dim <= 0 || in_dim <= 0) return RECMV_E_SHAPE;
+  if (P == 0) return RECMV_OK;
+  if (!X || !W || !Y) return RECMV_E_NULL;
+  if (act < 0 || act > 2) return RECMV_E_DTYPE;
+  if (P > (int64_t)1 << 30) return RECMV_E_RANGE;
+  G3Params prm = {};
+  G3Task& t = prm.t[0];
+  t.A = X; t.lda = ldx; t.a_transposed = 0;
+  t.B = W; t.ldb = in_dim; t.b_transposed = 0;   // element (n = output row, k = input column) at W[n * in_dim + k]
+  t.bias = bias;
+  t.D = Y; t.ldd = ldy; t.D2 = Y2; t.ldd2 = ldy2;
+  t.M = (int)P; t.N = out_dim; t.K = in_dim;
+  t.split = (split > 0 && split < out_dim) ? split : out_dim;
+  t.a_scale = kActScale; t.b_scale = kWgtScale; t.d_scale = pre_scale;
+  t.epi = EPI_FWD_NONE + act;
+  int tiles = 0;
+  g3_set_tiles(t, tiles);
+  prm.ntasks = 1; prm.chunk_kb = 1 << 20; prm.dyn_scale = nullptr;
+  return g3_launch(prm, tiles, (cudaStream_t)stream);
+}
+
+extern "C" int recmv_pe_forward(const float* x, const float* pe_w, int bands, float* out, int64_t ld, float* out2,
+                                int64_t ld2, int64_t P, recmv_stream_t stream) {
+  if (P < 0 || bands < 0 || bands > 6) return RECMV_E_SHAPE;
+  if (P == 0) return RECMV_OK;
+  if (!x || !pe_w || !out) return RECMV_E_NULL;
+  PeWeights pw;
+  for (int i = 0; i < 12; ++i) pw.w[i] = i < 2 * bands ? pe_w[i] : 0.f;
+  pe_forward_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, pw, bands, out, ld, out2, ld2, P);
+  return launch_status();
+}
 
 // --------------------------------------------------------------------------------------------------------------------
 // C ABI (include/recmv_b200.h): generic layer description, so the three networks share the two entry points
@@ -427,7 +517,7 @@ extern "C" int recmv_mlp_bwd_data_layer(const float* G, int64_t ldg, const float
   G3Params prm = {};
   G3Task& t = prm.t[0];
   t.A = G; t.lda = ldg; t.a_transposed = 0;
-  t.B = W; t.ldb = in_dim;                     // element (n = input column, k = output row) at W[k * in_dim + n]
+  t.B = W; t.ldb = in_dim; t.b_transposed = 1; // element (n = input column, k = output row) at W[k * in_dim + n]
   t.D = G_prev; t.ldd = ldgp; t.D2 = D2; t.ldd2 = ldd2;
   t.E = saved_input; t.lde = lds;
   t.M = (int)P; t.N = in_dim; t.K = out_dim;
@@ -453,7 +543,7 @@ extern "C" int recmv_mlp_bwd_weight(int num_layers, const float* const* G, const
     if (!G[l] || !X[l] || !dW[l]) return RECMV_E_NULL;
     G3Task& t = prm.t[l];
     t.A = G[l]; t.lda = ldg[l]; t.a_transposed = 1;     // element (m = output row, k = sample) at G[k * ldg + m]
-    t.B = X[l]; t.ldb = ldx[l];                          // element (n = input column, k = sample) at X[k * ldx + n]
+    t.B = X[l]; t.ldb = ldx[l]; t.b_transposed = 1;     // element (n = input column, k = sample) at X[k * ldx + n]
     t.D = dW[l]; t.ldd = in_dim[l]; t.D2 = nullptr; t.E = nullptr;
     t.colsum = db ? db[l] : nullptr;
     t.M = out_dim[l]; t.N = in_dim[l]; t.K = P; t.split = in_dim[l];

@@ -1,26 +1,29 @@
-// Marching cubes with shared vertices -- deterministic count / scan / emit.
+// Marching cubes with shared vertices -- deterministic sign-mask / count / scan / emit.
 // Replaces MCGpu/CudaKernels.cu:316-521 (d_mc_get_mesh_on_gpu, d_conver_ijkd_to_pindex, d_set_int,
 // d_scale_vertices) and the MCGpu singleton (CudaKernels.cu:524-639).
 //
 // Reference cost per call: memset of 3*N ints (-1), case tables in global memory, two global atomics
 // per triangle, output buffers sized to 5 % of the cells with no overflow check, blocking D2H copy.
-// Here: HBM-bound sweep.  Algorithmic bytes = 4 B x N (one read of the grid) + 12 B x V + 24 B x F.
-//   pass 1 (count): one read of the grid -> 1-byte case index per voxel + per-CTA (verts, tris) sums
-//   pass 2 (scan) : exclusive scan of the per-CTA sums (one CTA), totals -> host
-//   pass 3 (verts): case bytes -> CTA-local exclusive scan -> owned-edge vertices (v*step+origin) and a
-//                   packed (first vertex id, rank of edges 0/3/8) word for ACTIVE cells only (no memset:
-//                   only entries that were written are ever read)
-//   pass 4 (faces): case bytes -> scan -> int64 faces, neighbours' vertex ids from the packed words
+// Here: ONE read of the grid, then everything works on a 1-bit-per-voxel sign mask (N / 8 bytes, L2 resident):
+//   pass 0 (signs): coalesced read of the grid -> ballot -> bit t of word w = (sdf[32 w + t] < iso)        [HBM bound]
+//   pass 1 (count): one lane per run of 32 consecutive cells: the eight corner masks of the run are 8 funnel-shifted
+//                   words of the sign mask; cells with mixed signs = (OR of the masks) & ~(AND of the masks) -- 98 % of
+//                   the runs are done after ~40 instructions for 32 cells; only surface cells index the case tables
+//   pass 2 (scan) : exclusive scan of the per-segment (verts, tris) sums (one CTA); totals stay on the device
+//   pass 3 (verts): same decode -> warp scan -> owned-edge vertices (v*step+origin) and a packed (first vertex id,
+//                   rank of edges 0/3/8) word for ACTIVE cells only (no memset: only written entries are ever read)
+//   pass 4 (faces): same decode -> warp scan -> int64 faces, neighbours' vertex ids from the packed words
+// Algorithmic bytes = 4 B x N (one read of the grid) + 12 B x V + 24 B x F.
 // Output order = the order a sequential sweep of the reference kernel would produce (cells by linear
 // index, vertices by first appearance in the cell's triangle list), so results are reproducible and
-// comparable index-for-index with the CPU restatement (oracle/mc_oracle.c).
+// comparable index-for-index with the CPU restatement (oracle/mc_oracle.c); against the reference kernel's own
+// (atomics-ordered) output they are bit-identical after canonical ordering (tests/golden/mc_ref.npz).
 #include "common.cuh"
 #include "mc_tables.h"
 
 namespace recmv {
 
-constexpr int kMcThreads = 1024;
-
+constexpr int kMcThreads = 1024;   // cells per segment (one warp: 32 lanes x 32 consecutive cells)
 // Division of a 31-bit index by a runtime constant through a precomputed multiplier (Granlund-Montgomery):
 // the per-cell (i,j,k) decomposition otherwise costs two ~20-instruction integer divisions per cell.
 struct FastDiv {
@@ -120,57 +123,92 @@ __device__ __forceinline__ int2 block_excl_scan(int2 v, int2* tot) {
 
 constexpr int kMcWarpBlock = 256;  // 8 warps per CTA in the warp-per-segment passes
 
-// Pass 1, one WARP per 1024-cell segment, 32 rows of 32 consecutive cells: 4 coalesced loads per cell (its
-// four z-columns at k); the k+1 values come from the next lane by shuffle (lane 31 loads them).  No block
-// barrier, no shared memory.  Writes the 1-byte case index of every voxel and the segment's (verts, tris).
-__global__ void __launch_bounds__(kMcWarpBlock) mc_count_kernel(const float* __restrict__ sdf, int NX,
-                                                                int NY, int NZ, float iso,
-                                                                unsigned char* __restrict__ cube,
+// Pass 0: sign mask.  words = ceil(N / 32) + 2 (two zero words of padding so 64-bit windows never run off the end).
+__global__ void __launch_bounds__(256) mc_sign_kernel(const float* __restrict__ sdf, unsigned N, float iso,
+                                                      unsigned* __restrict__ bits, unsigned nwords) {
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = (blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * (unsigned)blockDim.x) >> 5;
+  // 4 words per warp iteration: four independent coalesced 128-byte loads in flight per lane
+  for (unsigned w0 = warp * 4; w0 < nwords; w0 += nwarps * 4) {
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned idx = (w0 + q) * 32u + lane;
+      v[q] = idx < N ? __ldg(sdf + idx) : iso;          // padding: not below the iso value -> bit 0
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned b = __ballot_sync(0xffffffffu, v[q] < iso);
+      if (lane == q && w0 + q < nwords) bits[w0 + q] = b;
+    }
+  }
+}
+
+// The eight corner masks of the 32 cells [b, b + 32): bit t of m[c] = sign of corner c of cell b + t, corners in the
+// cube-index bit order of the reference (CudaKernels.cu:316-360): (i,j,k) (i+1,j,k) (i+1,j+1,k) (i,j+1,k), then k+1.
+struct RunMasks { unsigned m[8]; unsigned active; };
+__device__ __forceinline__ unsigned bit_window(const unsigned* __restrict__ bits, unsigned pos) {
+  const unsigned w = pos >> 5;
+  return __funnelshift_r(__ldg(bits + w), __ldg(bits + w + 1), pos & 31u);
+}
+__device__ __forceinline__ RunMasks decode_run(const unsigned* __restrict__ bits, unsigned b, unsigned NZ, unsigned plane) {
+  RunMasks r;
+  const unsigned off[4] = {0u, plane, plane + NZ, NZ};
+  unsigned any = 0u, all = 0xffffffffu;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    r.m[q] = bit_window(bits, b + off[q]);
+    r.m[q + 4] = bit_window(bits, b + off[q] + 1u);
+    any |= r.m[q] | r.m[q + 4];
+    all &= r.m[q] & r.m[q + 4];
+  }
+  r.active = any & ~all;
+  return r;
+}
+__device__ __forceinline__ int cube_index(const RunMasks& r, int t) {
+  int ci = 0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) ci |= (int)((r.m[c] >> t) & 1u) << c;
+  return ci;
+}
+// (i, j, k) of a flat index and whether it is the base corner of a cell
+__device__ __forceinline__ bool cell_coords(unsigned idx, unsigned N, int NX, int NY, int NZ, unsigned plane,
+                                            const FastDiv& dplane, const FastDiv& dnz, int& i, int& j, int& k) {
+  i = (int)dplane.div(idx);
+  const unsigned rem = idx - (unsigned)i * plane;
+  j = (int)dnz.div(rem);
+  k = (int)(rem - (unsigned)j * (unsigned)NZ);
+  return idx < N && i < NX - 1 && j < NY - 1 && k < NZ - 1;
+}
+
+// Pass 1: one warp per 1024-cell segment (lane L owns cells seg*1024 + 32 L .. + 31): (verts, tris) of the segment.
+__global__ void __launch_bounds__(kMcWarpBlock) mc_count_kernel(const unsigned* __restrict__ bits, int NX, int NY, int NZ,
                                                                 int2* __restrict__ block_sums, int nseg,
                                                                 FastDiv dplane, FastDiv dnz) {
   const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
   const int lane = threadIdx.x & 31;
   const int seg = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (seg >= nseg) return;
+  const unsigned b = (unsigned)seg * kMcThreads + 32u * lane;
   int acc = 0;  // verts | tris << 16 of this lane
-  const size_t sj = NZ, si = plane;
-#pragma unroll 4
-  for (int r = 0; r < 32; ++r) {
-    const unsigned idx = (unsigned)seg * kMcThreads + r * 32 + lane;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // columns (i,j) (i+1,j) (i+1,j+1) (i,j+1) at k
-    bool cell = false;
-    unsigned i = 0, j = 0, k = 0;
-    if (idx < N) {
-      i = dplane.div(idx);
-      const unsigned rem = idx - i * plane;
-      j = dnz.div(rem);
-      k = rem - j * NZ;
-      const bool col = i < (unsigned)NX - 1 && j < (unsigned)NY - 1;
-      if (col) {
-        const float* p = sdf + idx;
-        a0 = __ldg(p); a1 = __ldg(p + si); a2 = __ldg(p + si + sj); a3 = __ldg(p + sj);
-      }
-      cell = col && k < (unsigned)NZ - 1;
+  if (b < N) {
+    RunMasks r = decode_run(bits, b, (unsigned)NZ, plane);
+    unsigned a = r.active;
+    while (a) {
+      const int t = __ffs(a) - 1;
+      a &= a - 1;
+      int i, j, k;
+      if (!cell_coords(b + t, N, NX, NY, NZ, plane, dplane, dnz, i, j, k)) continue;
+      const int ci = cube_index(r, t);
+      acc += (c_mc.vinfo[ci] >> 6) | ((int)c_mc.ntri[ci] << 16);
     }
-    // k+1 values: lane+1 holds idx+1 (same column unless the row wraps, and then this cell is not a cell)
-    float b0 = __shfl_down_sync(0xffffffffu, a0, 1), b1 = __shfl_down_sync(0xffffffffu, a1, 1);
-    float b2 = __shfl_down_sync(0xffffffffu, a2, 1), b3 = __shfl_down_sync(0xffffffffu, a3, 1);
-    if (lane == 31 && cell) {
-      const float* p = sdf + idx + 1;
-      b0 = __ldg(p); b1 = __ldg(p + si); b2 = __ldg(p + si + sj); b3 = __ldg(p + sj);
-    }
-    int ci = 0;
-    if (cell) {
-      ci = (a0 < iso) | ((a1 < iso) << 1) | ((a2 < iso) << 2) | ((a3 < iso) << 3) | ((b0 < iso) << 4) |
-           ((b1 < iso) << 5) | ((b2 < iso) << 6) | ((b3 < iso) << 7);
-      if (ci != 0 && ci != 255) acc += (c_mc.vinfo[ci] >> 6) | ((int)c_mc.ntri[ci] << 16);
-    }
-    if (idx < N) cube[idx] = (unsigned char)ci;
   }
   const int tot = __reduce_add_sync(0xffffffffu, acc);
   if (lane == 0) block_sums[seg] = make_int2(tot & 0xffff, tot >> 16);
 }
 
+// totals[0] = V, totals[1] = F, totals[2] = overflow flag (set by the emit passes), totals[3] = 0
 __global__ void __launch_bounds__(kMcThreads) mc_scan_kernel(int2* __restrict__ block_sums, int nb,
                                                              int* __restrict__ totals) {
   __shared__ int2 tot;
@@ -183,7 +221,7 @@ __global__ void __launch_bounds__(kMcThreads) mc_scan_kernel(int2* __restrict__ 
     carry.x += tot.x; carry.y += tot.y;
     __syncthreads();
   }
-  if (threadIdx.x == 0) { totals[0] = carry.x; totals[1] = carry.y; }
+  if (threadIdx.x == 0) { totals[0] = carry.x; totals[1] = carry.y; totals[2] = 0; totals[3] = 0; }
 }
 
 // (iso - v1) / (v2 - v1) evaluated like d_fGetOffset (CudaKernels.cu:304-314): float differences,
@@ -206,94 +244,103 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
   return inc - v;
 }
 
-// Passes 3 and 4, one warp per 1024-cell segment, 8 rows of 128 cells: each lane loads the case bytes of 4
-// consecutive cells as one 32-bit word; a row whose words are all 0x00000000 / 0xffffffff (no surface: ~98 %
-// of them) costs one load and one ballot.
+// Passes 3 and 4, one warp per segment, same decode as the count pass.  `cap` = capacity (rows) of the output buffer:
+// a segment whose rows would not fit sets totals[2] and writes nothing (the host grows the buffer and re-runs).
 template <bool kFaces>
 __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
     const float* __restrict__ sdf, int NX, int NY, int NZ, float iso,
-    const unsigned char* __restrict__ cube, const int2* __restrict__ block_offs,
+    const unsigned* __restrict__ bits, const int2* __restrict__ block_offs,
     int* __restrict__ cellinfo, float sx, float sy, float sz, float ox, float oy, float oz,
-    float* __restrict__ verts, long long* __restrict__ faces, int nseg, FastDiv dplane, FastDiv dnz) {
+    float* __restrict__ verts, long long* __restrict__ faces, long long cap, int* __restrict__ totals, int nseg,
+    FastDiv dplane, FastDiv dnz) {
   const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
   const int lane = threadIdx.x & 31;
   const int seg = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (seg >= nseg) return;
   const int2 segoff = block_offs[seg];
-  if (!kFaces) { if (seg + 1 < nseg && block_offs[seg + 1].x == segoff.x) return; }   // nothing to emit here
-  else { if (seg + 1 < nseg && block_offs[seg + 1].y == segoff.y) return; }
-  int running = kFaces ? segoff.y : segoff.x;
-  for (int r = 0; r < 8; ++r) {
-    const unsigned idx0 = (unsigned)seg * kMcThreads + r * 128 + lane * 4;
-    unsigned word = 0;
-    if (idx0 + 3 < N) word = *reinterpret_cast<const unsigned*>(cube + idx0);   // N*1 bytes; idx0 % 4 == 0
-    else { for (int q = 0; q < 4; ++q) if (idx0 + q < N) word |= (unsigned)cube[idx0 + q] << (8 * q); }
-    if (__ballot_sync(0xffffffffu, word != 0u && word != 0xffffffffu) == 0u) continue;
-    int cnt[4], mine = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ci = (word >> (8 * q)) & 255;
-      cnt[q] = (ci != 0 && ci != 255) ? (kFaces ? (int)c_mc.ntri[ci] : (int)(c_mc.vinfo[ci] >> 6)) : 0;
-      mine += cnt[q];
+  const int seg_end = seg + 1 < nseg ? (kFaces ? block_offs[seg + 1].y : block_offs[seg + 1].x)
+                                     : (kFaces ? totals[1] : totals[0]);
+  const int seg_begin = kFaces ? segoff.y : segoff.x;
+  if (seg_end == seg_begin) return;   // nothing to emit here
+  if ((long long)seg_end > cap) { if (lane == 0) totals[2] = 1; return; }
+  const unsigned b = (unsigned)seg * kMcThreads + 32u * lane;
+  RunMasks r;
+  r.active = 0u;
+  if (b < N) r = decode_run(bits, b, (unsigned)NZ, plane);
+  // first sweep over my active cells: how many rows do I emit
+  int mine = 0;
+  {
+    unsigned a = r.active;
+    while (a) {
+      const int t = __ffs(a) - 1;
+      a &= a - 1;
+      int i, j, k;
+      if (!cell_coords(b + t, N, NX, NY, NZ, plane, dplane, dnz, i, j, k)) { r.active &= ~(1u << t); continue; }
+      const int ci = cube_index(r, t);
+      mine += kFaces ? (int)c_mc.ntri[ci] : (int)(c_mc.vinfo[ci] >> 6);
     }
-    int row_total;
-    int off = running + warp_excl_scan(mine, lane, &row_total);
-    running += row_total;
-    if (mine == 0) continue;
+  }
+  int row_total;
+  int off = seg_begin + warp_excl_scan(mine, lane, &row_total);
+  unsigned a = r.active;   // invalid "cells" were removed above
+  while (a) {
+    const int t = __ffs(a) - 1;
+    a &= a - 1;
+    const unsigned idx = b + t;
+    int i, j, k;
+    cell_coords(idx, N, NX, NY, NZ, plane, dplane, dnz, i, j, k);
+    const int ci = cube_index(r, t);
+    if (!kFaces) {
+      const int info = c_mc.vinfo[ci];
+      const int cnt = info >> 6;
+      if (cnt == 0) continue;
+      const int vbase = off;
+      cellinfo[idx] = (vbase << 6) | (info & 63);
+      const float* p = sdf + idx;
+      const float v0 = __ldg(p);
+      const float fX = (float)i, fY = (float)j, fZ = (float)k;
+      const int r0 = info & 3, r3 = (info >> 2) & 3, r8 = (info >> 4) & 3;
+      if (r0 != 3) {  // edge 0: corner 0 -> 1, +x
+        const float o_ = edge_offset(v0, __ldg(p + plane), iso);
+        float* o = verts + (size_t)(vbase + r0) * 3;
+        o[0] = fmaf(fX + o_, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ, sz, oz);
+      }
+      if (r3 != 3) {  // edge 3: corner 3 (0,1,0) -> 0, -y
+        const float o_ = edge_offset(__ldg(p + NZ), v0, iso);
+        float* o = verts + (size_t)(vbase + r3) * 3;
+        o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY + (1.f - o_), sy, oy); o[2] = fmaf(fZ, sz, oz);
+      }
+      if (r8 != 3) {  // edge 8: corner 0 -> 4, +z
+        const float o_ = edge_offset(v0, __ldg(p + 1), iso);
+        float* o = verts + (size_t)(vbase + r8) * 3;
+        o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ + o_, sz, oz);
+      }
+      off += cnt;
+    } else {
+      const int cnt = c_mc.ntri[ci];
+      const long long fbase = off;
+      for (int tt = 0; tt < cnt; ++tt) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (cnt[q] == 0) continue;
-      const unsigned idx = idx0 + q;
-      const int ci = (word >> (8 * q)) & 255;
-      const int i = (int)dplane.div(idx), rem = (int)(idx - (unsigned)i * plane);
-      const int j = (int)dnz.div((unsigned)rem), k = rem - j * NZ;
-      if (!kFaces) {
-        const int info = c_mc.vinfo[ci];
-        const int vbase = off;
-        cellinfo[idx] = (vbase << 6) | (info & 63);
-        const float* p = sdf + idx;
-        const float v0 = __ldg(p);
-        const float fX = (float)i, fY = (float)j, fZ = (float)k;
-        const int r0 = info & 3, r3 = (info >> 2) & 3, r8 = (info >> 4) & 3;
-        if (r0 != 3) {  // edge 0: corner 0 -> 1, +x
-          const float o_ = edge_offset(v0, __ldg(p + plane), iso);
-          float* o = verts + (size_t)(vbase + r0) * 3;
-          o[0] = fmaf(fX + o_, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ, sz, oz);
-        }
-        if (r3 != 3) {  // edge 3: corner 3 (0,1,0) -> 0, -y
-          const float o_ = edge_offset(__ldg(p + NZ), v0, iso);
-          float* o = verts + (size_t)(vbase + r3) * 3;
-          o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY + (1.f - o_), sy, oy); o[2] = fmaf(fZ, sz, oz);
-        }
-        if (r8 != 3) {  // edge 8: corner 0 -> 4, +z
-          const float o_ = edge_offset(v0, __ldg(p + 1), iso);
-          float* o = verts + (size_t)(vbase + r8) * 3;
-          o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ + o_, sz, oz);
-        }
-      } else {
-        const long long fbase = off;
-        for (int t = 0; t < cnt[q]; ++t) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const int e = g_mc_tri[ci][3 * t + c];
-            const int oi = i + c_mc.owner[e][0], oj = j + c_mc.owner[e][1], ok = k + c_mc.owner[e][2];
-            const int d = c_mc.owner[e][3];
-            long long vid = -1;
-            if (oi < NX - 1 && oj < NY - 1 && ok < NZ - 1) {
-              const int info = cellinfo[((int64_t)oi * NY + oj) * NZ + ok];
-              vid = (long long)(info >> 6) + ((info >> (2 * d)) & 3);
-            }
-            faces[(fbase + t) * 3 + (2 - c)] = vid;  // reversed winding (CudaKernels.cu:502)
+        for (int c = 0; c < 3; ++c) {
+          const int e = g_mc_tri[ci][3 * tt + c];
+          const int oi = i + c_mc.owner[e][0], oj = j + c_mc.owner[e][1], ok = k + c_mc.owner[e][2];
+          const int d = c_mc.owner[e][3];
+          long long vid = -1;
+          if (oi < NX - 1 && oj < NY - 1 && ok < NZ - 1) {
+            const int info = cellinfo[((int64_t)oi * NY + oj) * NZ + ok];
+            vid = (long long)(info >> 6) + ((info >> (2 * d)) & 3);
           }
+          faces[(fbase + tt) * 3 + (2 - c)] = vid;  // reversed winding (CudaKernels.cu:502)
         }
       }
-      off += cnt[q];
+      off += cnt;
     }
   }
 }
 
 struct McScratch {
-  unsigned char* cube;
+  unsigned* bits;      // sign mask, nwords words
+  unsigned nwords;
   int* cellinfo;
   int2* block_sums;
   int* totals;
@@ -307,7 +354,8 @@ static McScratch carve(void* scratch, int NX, int NY, int NZ) {
   McScratch s;
   s.nb = (int)((N + kMcThreads - 1) / kMcThreads);
   char* p = (char*)scratch;
-  s.cube = (unsigned char*)p; p += align256((size_t)N);
+  s.nwords = (unsigned)((N + 31) / 32 + 2);
+  s.bits = (unsigned*)p; p += align256((size_t)s.nwords * 4);
   s.cellinfo = (int*)p; p += align256((size_t)N * 4);
   s.block_sums = (int2*)p; p += align256((size_t)s.nb * 8);
   s.totals = (int*)p;
@@ -324,26 +372,64 @@ extern "C" int recmv_mc_scratch_bytes(int NX, int NY, int NZ, size_t* bytes) {
   int64_t N = (int64_t)NX * NY * NZ;
   if (N > 2000000000LL) return RECMV_E_RANGE;
   int nb = (int)((N + kMcThreads - 1) / kMcThreads);
-  *bytes = align256((size_t)N) + align256((size_t)N * 4) + align256((size_t)nb * 8) + 256;
+  *bytes = align256((size_t)((N + 31) / 32 + 2) * 4) + align256((size_t)N * 4) + align256((size_t)nb * 8) + 256;
   return RECMV_OK;
 }
 
-extern "C" int recmv_mc_count(const float* sdf, int NX, int NY, int NZ, float iso, void* scratch,
-                              int64_t* num_verts, int64_t* num_faces, recmv_stream_t stream) {
-  if (!sdf || !scratch || !num_verts || !num_faces) return RECMV_E_NULL;
+namespace {
+int mc_check(const float* sdf, const void* scratch, int NX, int NY, int NZ) {
+  if (!sdf || !scratch) return RECMV_E_NULL;
   if (NX <= 0 || NY <= 0 || NZ <= 0) return RECMV_E_SHAPE;
   if ((int64_t)NX * NY * NZ > 2000000000LL) return RECMV_E_RANGE;
-  int s = ensure_tables();
+  return ensure_tables();
+}
+
+// passes 0-2: sign mask, per-segment counts, scan (totals stay on the device)
+int mc_classify(const float* sdf, int NX, int NY, int NZ, float iso, const McScratch& sc, cudaStream_t st) {
+  const unsigned N = (unsigned)((int64_t)NX * NY * NZ);
+  mc_sign_kernel<<<stride_grid((int64_t)sc.nwords * 8, 256, 8), 256, 0, st>>>(sdf, N, iso, sc.bits, sc.nwords);
+  int s = launch_status();
   if (s) return s;
-  cudaStream_t st = (cudaStream_t)stream;
-  McScratch sc = carve(scratch, NX, NY, NZ);
   const int grid = (sc.nb * 32 + kMcWarpBlock - 1) / kMcWarpBlock;  // one warp per 1024-cell segment
   const FastDiv dplane = FastDiv::make((unsigned)NY * NZ), dnz = FastDiv::make((unsigned)NZ);
-  mc_count_kernel<<<grid, kMcWarpBlock, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums, sc.nb, dplane, dnz);
+  mc_count_kernel<<<grid, kMcWarpBlock, 0, st>>>(sc.bits, NX, NY, NZ, sc.block_sums, sc.nb, dplane, dnz);
   s = launch_status();
   if (s) return s;
   mc_scan_kernel<<<1, kMcThreads, 0, st>>>(sc.block_sums, sc.nb, sc.totals);
-  s = launch_status();
+  return launch_status();
+}
+
+int mc_emit_passes(const float* sdf, int NX, int NY, int NZ, float iso, const McScratch& sc, const float step[3],
+                   const float origin[3], float* verts, int64_t cap_v, int64_t* faces, int64_t cap_f, cudaStream_t st) {
+  const int grid = (sc.nb * 32 + kMcWarpBlock - 1) / kMcWarpBlock;
+  const FastDiv dplane = FastDiv::make((unsigned)NY * NZ), dnz = FastDiv::make((unsigned)NZ);
+  if (verts) {
+    mc_emit_kernel<false><<<grid, kMcWarpBlock, 0, st>>>(sdf, NX, NY, NZ, iso, sc.bits, sc.block_sums, sc.cellinfo,
+                                                         step[0], step[1], step[2], origin[0], origin[1], origin[2],
+                                                         verts, nullptr, cap_v, sc.totals, sc.nb, dplane, dnz);
+    int s = launch_status();
+    if (s) return s;
+  }
+  if (faces) {
+    if (!verts) return RECMV_E_NULL;  // faces need the packed words written by the vertex pass
+    mc_emit_kernel<true><<<grid, kMcWarpBlock, 0, st>>>(sdf, NX, NY, NZ, iso, sc.bits, sc.block_sums, sc.cellinfo,
+                                                        0.f, 0.f, 0.f, 0.f, 0.f, 0.f, nullptr, (long long*)faces, cap_f,
+                                                        sc.totals, sc.nb, dplane, dnz);
+    int s = launch_status();
+    if (s) return s;
+  }
+  return RECMV_OK;
+}
+}  // namespace
+
+extern "C" int recmv_mc_count(const float* sdf, int NX, int NY, int NZ, float iso, void* scratch,
+                              int64_t* num_verts, int64_t* num_faces, recmv_stream_t stream) {
+  if (!num_verts || !num_faces) return RECMV_E_NULL;
+  int s = mc_check(sdf, scratch, NX, NY, NZ);
+  if (s) return s;
+  cudaStream_t st = (cudaStream_t)stream;
+  McScratch sc = carve(scratch, NX, NY, NZ);
+  s = mc_classify(sdf, NX, NY, NZ, iso, sc, st);
   if (s) return s;
   int h[2] = {0, 0};
   cudaError_t e = cudaMemcpyAsync(h, sc.totals, sizeof(h), cudaMemcpyDeviceToHost, st);
@@ -358,28 +444,31 @@ extern "C" int recmv_mc_count(const float* sdf, int NX, int NY, int NZ, float is
 extern "C" int recmv_mc_emit(const float* sdf, int NX, int NY, int NZ, float iso, void* scratch,
                              const float step[3], const float origin[3], float* verts,
                              int64_t* faces, recmv_stream_t stream) {
-  if (!sdf || !scratch || !step || !origin) return RECMV_E_NULL;
-  if (NX <= 0 || NY <= 0 || NZ <= 0) return RECMV_E_SHAPE;
-  int s = ensure_tables();
+  if (!step || !origin) return RECMV_E_NULL;
+  int s = mc_check(sdf, scratch, NX, NY, NZ);
+  if (s) return s;
+  // buffers were sized from recmv_mc_count's totals: no capacity limit
+  return mc_emit_passes(sdf, NX, NY, NZ, iso, carve(scratch, NX, NY, NZ), step, origin, verts, (int64_t)1 << 40, faces,
+                        (int64_t)1 << 40, (cudaStream_t)stream);
+}
+
+// One call, no host synchronisation: classify + count + scan + emit into caller-provided buffers of capacity
+// (cap_verts, cap_faces) rows.  counts (device, int32[4]) receives {V, F, overflow, 0}: with overflow != 0 at least one of
+// the buffers was too small -- rows that did fit are valid, the caller re-runs with buffers of (V, F) rows.
+extern "C" int recmv_mc_run(const float* sdf, int NX, int NY, int NZ, float iso, void* scratch, const float step[3],
+                            const float origin[3], float* verts, int64_t cap_verts, int64_t* faces, int64_t cap_faces,
+                            int32_t* counts, recmv_stream_t stream) {
+  if (!step || !origin || !counts || !verts || !faces) return RECMV_E_NULL;
+  if (cap_verts < 0 || cap_faces < 0) return RECMV_E_SHAPE;
+  int s = mc_check(sdf, scratch, NX, NY, NZ);
   if (s) return s;
   cudaStream_t st = (cudaStream_t)stream;
   McScratch sc = carve(scratch, NX, NY, NZ);
-  const int grid = (sc.nb * 32 + kMcWarpBlock - 1) / kMcWarpBlock;
-  const FastDiv dplane = FastDiv::make((unsigned)NY * NZ), dnz = FastDiv::make((unsigned)NZ);
-  if (verts) {
-    mc_emit_kernel<false><<<grid, kMcWarpBlock, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums, sc.cellinfo,
-                                                         step[0], step[1], step[2], origin[0], origin[1], origin[2],
-                                                         verts, nullptr, sc.nb, dplane, dnz);
-    s = launch_status();
-    if (s) return s;
-  }
-  if (faces) {
-    if (!verts) return RECMV_E_NULL;  // faces need the packed words written by the vertex pass
-    mc_emit_kernel<true><<<grid, kMcWarpBlock, 0, st>>>(sdf, NX, NY, NZ, iso, sc.cube, sc.block_sums, sc.cellinfo,
-                                                        0.f, 0.f, 0.f, 0.f, 0.f, 0.f, nullptr, (long long*)faces,
-                                                        sc.nb, dplane, dnz);
-    s = launch_status();
-    if (s) return s;
-  }
-  return RECMV_OK;
+  s = mc_classify(sdf, NX, NY, NZ, iso, sc, st);
+  if (s) return s;
+  const int64_t cv = cap_verts < (1 << 25) ? cap_verts : (1 << 25) - 1;   // packed vertex ids are 26 bit signed-safe
+  s = mc_emit_passes(sdf, NX, NY, NZ, iso, sc, step, origin, verts, cv, faces, cap_faces, st);
+  if (s) return s;
+  cudaError_t e = cudaMemcpyAsync(counts, sc.totals, 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+  return e == cudaSuccess ? RECMV_OK : (int)e;
 }

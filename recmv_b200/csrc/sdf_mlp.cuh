@@ -61,10 +61,6 @@ int tc_sdf_forward(const PointSource& src, const void* packed, const PeWeights& 
 // time-outs (code 1) and fp16 operand-range violations (code 2); see recmv_check_async_errors
 int device_status_record(void** out);
 
-// training forward: as tc_sdf_forward, and every layer's input is also saved (fp32) for the backward GEMMs
-int tc_sdf_forward_save(const float* x, const void* packed, const PeWeights& pw, float* out_sdf, float* out_feat,
-                        float* const* act, const int* act_ld, int64_t P, int passes, cudaStream_t st);
-
 // value + input gradient in one forward-mode launch (tcgen05 path only)
 int tc_sdf_forward_grad(const float* x, const void* packed, const PeWeights& pw, float* out_sdf, float* out_feat,
                         float* out_grad, int64_t P, int passes, cudaStream_t st);

@@ -310,23 +310,6 @@ extern "C" int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float
   return run_forward(src, packed, pe_w, out_sdf, out_feat, P, mode, (cudaStream_t)stream);
 }
 
-extern "C" int recmv_sdf_mlp_fwd_train(const float* x, const void* packed, const float* pe_w, float* out_sdf,
-                                       float* out_feat, float* const* act, const int* act_ld, int64_t P, int mode,
-                                       recmv_stream_t stream) {
-  if (P < 0) return RECMV_E_SHAPE;
-  if (P == 0) return RECMV_OK;
-  if (!x || !packed || !pe_w || !out_sdf || !act || !act_ld) return RECMV_E_NULL;
-  if (mode != RECMV_MLP_TC_F16X3 && mode != RECMV_MLP_TC_F16X1) return RECMV_E_UNSUPPORTED;
-  for (int l = 0; l < kNumLayers; ++l) {
-    if (!act[l]) return RECMV_E_NULL;
-    if (act_ld[l] < layer_in(l) || (act_ld[l] & 3) != 0) return RECMV_E_SHAPE;
-  }
-  PeWeights pw;
-  for (int i = 0; i < 12; ++i) pw.w[i] = pe_w[i];
-  return tc_sdf_forward_save(x, packed, pw, out_sdf, out_feat, act, act_ld, P, mode == RECMV_MLP_TC_F16X3 ? 3 : 1,
-                             (cudaStream_t)stream);
-}
-
 extern "C" int recmv_sdf_mlp_fwd_grad(const float* x, const void* packed, const float* pe_w, float* out_sdf,
                                       float* out_feat, float* out_grad, int64_t P, int mode,
                                       recmv_stream_t stream) {

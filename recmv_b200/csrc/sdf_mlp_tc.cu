@@ -109,11 +109,6 @@ struct TcParams {
   const float* view_dirs;        // [P,3]
   const float* feats;            // [P,256]
   float* out_rgb;                // [P,3]
-  // training forward (kSave): every layer's INPUT is also written to HBM in fp32 for the backward GEMMs (gemm3.cu):
-  // act[l] = [P][act_ld[l]] input of layer l.  SDF network: act[0] = PE (39 of 64), act[l] = softplus output of layer
-  // l-1, act[4] = [a_3 (473) | PE (39)] (the skip concatenation; its 1/sqrt2 lives in the packed weights)
-  float* act[9];
-  int act_ld[9];
 };
 #define TRACE(role, it, l, ev)                                                                     \
   do {                                                                                             \
@@ -215,10 +210,9 @@ template <> struct Net<2> {
 
 }  // namespace
 
-template <bool kJvp, int kNet, bool kSave = false>
+template <bool kJvp, int kNet>
 __global__ void __cluster_dims__(2 * kPairs, 1, 1) __launch_bounds__(kThreads, 1)
 sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
-  static_assert(!kSave || (!kJvp && kNet == 0), "activation saving exists for the plain SDF forward");
   using NetT = Net<kNet>;
   constexpr int kNumLayers = NetT::kLayers;   // shadows the SDF constant of common.cuh
   static_assert(!kJvp || kNet == 0 || kNet == 1, "the forward-mode variant exists for the SDF network and the deformer");
@@ -538,16 +532,6 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                 }
               }
               range_check8(v, prm.status, 1000 + l);
-              if (kSave && p < prm.P && f < (l == 3 ? kSkipOut : 512)) {   // layer 3 has 473 outputs (f is a multiple of 8)
-                float* dst = prm.act[l + 1] + (size_t)p * prm.act_ld[l + 1] + f;
-                constexpr float kInv = 1.f / kActScale;
-                if (l == 3 && f + 8 > kSkipOut) {
-                  for (int e = 0; e < kSkipOut - f; ++e) dst[e] = v[e] * kInv;
-                } else {
-                  *reinterpret_cast<float4*>(dst) = make_float4(v[0] * kInv, v[1] * kInv, v[2] * kInv, v[3] * kInv);
-                  *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] * kInv, v[5] * kInv, v[6] * kInv, v[7] * kInv);
-                }
-              }
               uint4 hi, lo;
               split8(v, hi, lo);
               const int kb = f >> 6, chunk = (f & 63) >> 3;
@@ -781,12 +765,6 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         } else {
           positional_encode_tangent(cx, cy, cz, (row & 3) - 1, prm.pw.w, pe);
         }
-        if (kSave) {
-          float* d0 = prm.act[0] + (size_t)p * prm.act_ld[0];
-          float* d4 = prm.act[4] + (size_t)p * prm.act_ld[4] + kSkipOut;
-#pragma unroll
-          for (int e = 0; e < 39; ++e) { d0[e] = pe[e]; d4[e] = pe[e]; }
-        }
 #pragma unroll
         for (int e = 0; e < 39; ++e) pe[e] *= kActScale;
       } else {
@@ -870,7 +848,6 @@ int tc_prepare_launch(int dev) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(sdf_tc_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return (int)e;
   done[dev & 15] = true;
   return 0;
@@ -899,7 +876,7 @@ int tc_max_clusters(int dev) {
 
 static int launch_tc(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
                      float* out_feat, float* out_grad, int64_t P, int passes, int dbg_layer, float* dbg_out, int* status_host,
-                     unsigned long long* trace, cudaStream_t st, float* const* act = nullptr, const int* act_ld = nullptr) {
+                     unsigned long long* trace, cudaStream_t st) {
   if (passes != 1 && passes != 3) return RECMV_E_DTYPE;
   PackedLayout L = packed_layout();
   const char* pb = (const char*)packed;
@@ -932,11 +909,7 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   int64_t want = (tiles + kPairs - 1) / kPairs;
   const int maxc = tc_max_clusters(dev);
   int clusters = (int)(want < maxc ? want : maxc);
-  if (act) {
-    for (int l = 0; l < 9; ++l) { prm.act[l] = act[l]; prm.act_ld[l] = act_ld[l]; }
-    if (out_grad) return RECMV_E_UNSUPPORTED;
-    sdf_tc_kernel<false, 0, true><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
-  } else if (out_grad)
+  if (out_grad)
     sdf_tc_kernel<true, 0><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
   else
     sdf_tc_kernel<false, 0><<<clusters * 2 * kPairs, kThreads, kSmemBytes, st>>>(tc_.m128, prm);
@@ -954,14 +927,6 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
 int tc_sdf_forward(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
                    float* out_feat, int64_t P, int passes, cudaStream_t st) {
   return launch_tc(src, packed, pw, out_sdf, out_feat, nullptr, P, passes, -1, nullptr, nullptr, nullptr, st);
-}
-
-int tc_sdf_forward_save(const float* x, const void* packed, const PeWeights& pw, float* out_sdf, float* out_feat,
-                        float* const* act, const int* act_ld, int64_t P, int passes, cudaStream_t st) {
-  PointSource src = {};
-  src.x = x;
-  src.S = 1;
-  return launch_tc(src, packed, pw, out_sdf, out_feat, nullptr, P, passes, -1, nullptr, nullptr, nullptr, st, act, act_ld);
 }
 
 int tc_sdf_forward_grad(const float* x, const void* packed, const PeWeights& pw, float* out_sdf, float* out_feat,

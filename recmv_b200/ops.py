@@ -214,12 +214,30 @@ def voxel_to_channels_last(ws):
 # --------------------------------------------------------------------------------------------------
 # MCGpu
 # --------------------------------------------------------------------------------------------------
-_mc_scratch = {}
+_mc_state = {}   # per device: grow-only scratch + output buffers (like the MCGpu singleton, MCGpu/CudaKernels.cu:524-604)
+
+
+def _mc_buffers(dev, nbytes, cap_v, cap_f):
+    st = _mc_state.setdefault(dev.index, {})
+    if st.get("scratch") is None or st["scratch"].numel() < nbytes:
+        st["scratch"] = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    if st.get("verts") is None or st["verts"].shape[0] < cap_v:
+        st["verts"] = torch.empty((cap_v, 3), dtype=torch.float32, device=dev)
+    if st.get("faces") is None or st["faces"].shape[0] < cap_f:
+        st["faces"] = torch.empty((cap_f, 3), dtype=torch.int64, device=dev)
+    if st.get("counts") is None:
+        st["counts"] = torch.zeros((4,), dtype=torch.int32, device=dev)
+        st["counts_host"] = torch.zeros((4,), dtype=torch.int32).pin_memory()
+    return st
 
 
 def mc_gpu(sdfs, xstep=1.0, ystep=1.0, zstep=1.0, xmin=0.0, ymin=0.0, zmin=0.0, fTargetValue=0.0):
     """MCGpu.mc_gpu(sdfs, steps, mins, iso) -> [verts [V,3] f32, faces [F,3] i64]
-    (MCGpu/MCGpu.cpp:20-56).  Wrong dtype returns [] exactly like the reference (:41-42)."""
+    (MCGpu/MCGpu.cpp:20-56).  Wrong dtype returns [] exactly like the reference (:41-42).
+
+    One C call queues every pass (sign mask, count, scan, vertices, faces) into grow-only capacity buffers; the single
+    host synchronisation is the read of (V, F) AFTER everything is queued (the reference blocks between its kernels,
+    CudaKernels.cu:628).  The results are fresh tensors, as the reference returns (MCGpu.cpp:49-54)."""
     _check_input(sdfs, "sdfs")
     if sdfs.dtype != torch.float32:
         return []
@@ -229,23 +247,49 @@ def mc_gpu(sdfs, xstep=1.0, ystep=1.0, zstep=1.0, xmin=0.0, ymin=0.0, zmin=0.0, 
     lib = _lib.load()
     nbytes = c_size_t(0)
     check(lib.recmv_mc_scratch_bytes(NX, NY, NZ, byref(nbytes)), "recmv_mc_scratch_bytes")
-    key = (sdfs.device.index, )
-    scratch = _mc_scratch.get(key)
-    if scratch is None or scratch.numel() < nbytes.value:  # grow-only, like the MCGpu singleton
-        scratch = torch.empty((nbytes.value,), dtype=torch.uint8, device=sdfs.device)
-        _mc_scratch[key] = scratch
+    dev = sdfs.device
+    prev = _mc_state.get(dev.index, {})
+    cap_v = max(4096, prev["verts"].shape[0] if prev.get("verts") is not None else 0)
+    cap_f = max(8192, prev["faces"].shape[0] if prev.get("faces") is not None else 0)
+    step = (c_float * 3)(xstep, ystep, zstep)
+    org = (c_float * 3)(xmin, ymin, zmin)
+    with torch.cuda.device(dev):
+        stream = _stream(sdfs)
+        for _ in range(2):
+            st = _mc_buffers(dev, nbytes.value, cap_v, cap_f)
+            check(lib.recmv_mc_run(_ptr(sdfs), NX, NY, NZ, float(fTargetValue), _ptr(st["scratch"]), step, org,
+                                   _ptr(st["verts"]), st["verts"].shape[0], _ptr(st["faces"]), st["faces"].shape[0],
+                                   _ptr(st["counts"]), stream), "recmv_mc_run")
+            st["counts_host"].copy_(st["counts"], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            V, F, overflow = (int(v) for v in st["counts_host"][:3])
+            if V >= (1 << 25):
+                check(_lib.RECMV_E_RANGE, "recmv_mc_run (more than 2^25 vertices)")
+            if not overflow:
+                break
+            cap_v, cap_f = int(V * 1.25) + 1024, int(F * 1.25) + 2048   # grow once, re-run (buffers are kept)
+        else:
+            raise _lib.RecmvError("recmv_mc_run: output buffers still too small after growing")
+        return [st["verts"][:V].clone(), st["faces"][:F].clone()]
+
+
+def mc_gpu_two_call(sdfs, step=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), iso=0.0):
+    """The count / emit pair of the C ABI (exact-size outputs; synchronises between the two calls like the reference)."""
+    _check_input(sdfs, "sdfs")
+    NX, NY, NZ = sdfs.shape
+    lib = _lib.load()
+    nbytes = c_size_t(0)
+    check(lib.recmv_mc_scratch_bytes(NX, NY, NZ, byref(nbytes)), "recmv_mc_scratch_bytes")
+    scratch = torch.empty((nbytes.value,), dtype=torch.uint8, device=sdfs.device)
     V, F = c_int64(0), c_int64(0)
     with torch.cuda.device(sdfs.device):
         st = _stream(sdfs)
-        check(lib.recmv_mc_count(_ptr(sdfs), NX, NY, NZ, float(fTargetValue), _ptr(scratch), byref(V),
-                                 byref(F), st), "recmv_mc_count")
+        check(lib.recmv_mc_count(_ptr(sdfs), NX, NY, NZ, float(iso), _ptr(scratch), byref(V), byref(F), st), "recmv_mc_count")
         verts = torch.empty((V.value, 3), dtype=torch.float32, device=sdfs.device)
         faces = torch.empty((F.value, 3), dtype=torch.int64, device=sdfs.device)
         if V.value > 0:
-            step = (c_float * 3)(xstep, ystep, zstep)
-            org = (c_float * 3)(xmin, ymin, zmin)
-            check(lib.recmv_mc_emit(_ptr(sdfs), NX, NY, NZ, float(fTargetValue), _ptr(scratch), step,
-                                    org, _ptr(verts), _ptr(faces) if F.value > 0 else None, st),
+            check(lib.recmv_mc_emit(_ptr(sdfs), NX, NY, NZ, float(iso), _ptr(scratch), (c_float * 3)(*step),
+                                    (c_float * 3)(*origin), _ptr(verts), _ptr(faces) if F.value > 0 else None, st),
                   "recmv_mc_emit")
     return [verts, faces]
 
@@ -431,6 +475,26 @@ def mlp_bwd_weight(Gs, Xs, out_dims, in_dims, out_scales=None, dyn_scale=None, w
     return dW, db
 
 
+def mlp_fwd_layer(X, W, bias, out_dim, in_dim, act, Y, pre_scale=1.0, split=0, Y2=None):
+    """Y[:, :split or out] (and Y2) = act(pre_scale * X[:, :in] @ W.T + bias) on tcgen05 (training forward, one layer)."""
+    P = X.shape[0]
+    with torch.cuda.device(X.device):
+        check(_lib.load().recmv_mlp_fwd_layer(_ptr(X), X.stride(0), _ptr(W), _ptr(bias), int(out_dim), int(in_dim), int(act),
+                                              float(pre_scale), int(split), _ptr(Y), Y.stride(0), _ptr(Y2),
+                                              Y2.stride(0) if Y2 is not None else 0, P, _stream(X)), "recmv_mlp_fwd_layer")
+    return Y
+
+
+def pe_forward(x, pe_w, bands, out, out2=None):
+    """out[:, :3 + 6 bands] (and out2) = positional encoding of x [P,3] with annealing weights pe_w."""
+    w = (c_float * (2 * bands))(*[float(v) for v in pe_w[:2 * bands]])
+    with torch.cuda.device(x.device):
+        check(_lib.load().recmv_pe_forward(_ptr(x), w, int(bands), _ptr(out), out.stride(0), _ptr(out2),
+                                           out2.stride(0) if out2 is not None else 0, x.shape[0], _stream(x)),
+              "recmv_pe_forward")
+    return out
+
+
 def pe_backward(x, g, g2, pe_w, bands, dx=None):
     """dx (+)= (d PE/d x)^T (g + g2); g / g2 [P, >= 3 + 6 bands] (row stride free), x [P,3]."""
     P = x.shape[0]
@@ -467,16 +531,19 @@ def _sdf_composite(x, Ws, bs, pe_w):
 
 
 class SdfMlpTrainFunction(torch.autograd.Function):
-    """ImplicitNetwork.forward with gradients (model/network.py:89-119 inside train.py:317-330).
+    """ImplicitNetwork.forward with gradients (model/network.py:89-119 inside train.py:317-330), all GEMMs on tcgen05
+    in the engine's fp32-grade arithmetic (csrc/gemm3.cu: fp16 hi/lo split, 3 MMAs per product, fp32 accumulation).
 
-    forward : ONE fused tcgen05 launch (PE + 9 linears + softplus, activations on-chip) that also writes every layer's
-              input to HBM in fp32 (recmv_sdf_mlp_fwd_train) -- 16 KB per point, what autograd would keep anyway.
+    forward : PE kernel + 9 layer launches  Y = softplus(X W^T + b)  whose outputs stay in HBM as the next layer's input
+              AND as what the backward needs (16 KB per point -- what autograd keeps for the reference's graph); the skip
+              concatenation is a column range of layer 4's input buffer, its 1/sqrt2 a scale of that layer's GEMM.
+              (The inference engine keeps activations on-chip; a variant of it that also streamed them to HBM was
+              built and dropped: it fails above ~50 k points per call, profiles/r02_notes.md.)
     backward: first order (`loss.backward()`, parameter VJPs of propagateTmpPsGrad) -> 9 backward-data launches +
-              ONE weight-gradient launch + the PE Jacobian, all on tcgen05 in the engine's fp32-grade arithmetic
-              (csrc/gemm3.cu); weight-norm's (g, v) and anything upstream of x stay ordinary autograd.
-              Called with create_graph=True (eikonal / normals, network.py:121-133) the backward instead re-runs the
-              network as a torch graph over the saved inputs -- twice differentiable, on cuBLAS; `last_backward` says
-              which ran."""
+              ONE weight-gradient launch + the PE Jacobian; weight-norm's (g, v) and anything upstream of x stay
+              ordinary autograd.  Called with create_graph=True (eikonal / normals, network.py:121-133) the backward
+              instead re-runs the network as a torch graph over the saved inputs -- twice differentiable, on cuBLAS;
+              `last_backward` says which ran."""
     last_backward = None
 
     @staticmethod
@@ -486,16 +553,19 @@ class SdfMlpTrainFunction(torch.autograd.Function):
             raise RuntimeError("SdfMlpTrainFunction expects a contiguous float32 [P,3] tensor (convert outside, in the graph)")
         P = x.shape[0]
         dev = x.device
+        Ws = [w.detach().contiguous().float() for w in Ws]
+        bs = [b.detach().contiguous().float() for b in bs]
         act = [torch.empty((P, 64), dtype=torch.float32, device=dev)] + \
               [torch.empty((P, 512), dtype=torch.float32, device=dev) for _ in range(8)]
         sdf = torch.empty((P, 1), dtype=torch.float32, device=dev)
         feat = torch.empty((P, 256), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            check(_lib.load().recmv_sdf_mlp_fwd_train(_ptr(x), _ptr(packed), _pe_array(pe_w), _ptr(sdf), _ptr(feat),
-                                                      _ptr_array(act), (ctypes.c_int * 9)(*[a.stride(0) for a in act]),
-                                                      P, mode, _stream(x)), "recmv_sdf_mlp_fwd_train")
+        pe_forward(x, pe_w, 6, act[0], act[4][:, 473:])
+        for l in range(8):
+            mlp_fwd_layer(act[l], Ws[l], bs[l], Ws[l].shape[0], Ws[l].shape[1], ACT_SOFTPLUS100, act[l + 1],
+                          pre_scale=_INV_SQRT2 if l == 4 else 1.0)
+        mlp_fwd_layer(act[8], Ws[8], bs[8], 257, 512, ACT_NONE, sdf, split=1, Y2=feat)
         ctx.pe_w, ctx.mode = [float(w) for w in pe_w], mode
-        ctx.save_for_backward(x, *Ws, *bs, *act)
+        ctx.save_for_backward(x, *Wb, *act)
         return sdf, feat
 
     @staticmethod

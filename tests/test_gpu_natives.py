@@ -120,6 +120,22 @@ def test_marching_cubes_bit_exact_against_oracle(shape):
     assert np.array_equal(cf, of) and np.abs(cv - ov).max() < 1e-6
 
 
+def test_marching_cubes_two_call_abi_and_buffer_growth():
+    """recmv_mc_count + recmv_mc_emit (exact-size outputs) and the one-call path agree; the one-call path grows its
+    capacity buffers when the first guess is too small and is reproducible afterwards."""
+    ops._mc_state.clear()
+    big = synth.sphere_sdf_grid(97, num=6, seed=4, device=DEV)        # > 4096 vertices: forces one regrowth
+    v1, f1 = ops.mc_gpu(big, 2 / 96, 2 / 96, 2 / 96, -1.0, -1.0, -1.0)
+    assert v1.shape[0] > 4096
+    v2, f2 = ops.mc_gpu_two_call(big, (2 / 96,) * 3, (-1.0,) * 3, 0.0)
+    v3, f3 = ops.mc_gpu(big, 2 / 96, 2 / 96, 2 / 96, -1.0, -1.0, -1.0)
+    assert torch.equal(v1, v2) and torch.equal(f1, f2) and torch.equal(v1, v3) and torch.equal(f1, f3)
+    small = synth.sphere_sdf_grid(21, num=2, seed=4, device=DEV)      # smaller than the grown buffers: sliced, not stale
+    v4, f4 = ops.mc_gpu(small)
+    v5, f5 = ops.mc_gpu_two_call(small)
+    assert torch.equal(v4, v5) and torch.equal(f4, f5) and int(f4.max()) == v4.shape[0] - 1
+
+
 def test_marching_cubes_edge_cases_and_boundary_minus_one():
     assert ops.mc_gpu(torch.ones((5, 6, 7), device=DEV))[0].shape == (0, 3)
     assert ops.mc_gpu(-torch.ones((5, 6, 7), device=DEV))[1].shape == (0, 3)

@@ -323,7 +323,7 @@ def test_device_surface_solve_matches_reference_and_torch_loop():
     ps_t, ok_t, ms_t, n_t = run(False)
     print(f"device solve: {ms_d:.2f} ms, {n_d} launches | torch loop: {ms_t:.2f} ms, {n_t} launches | "
           f"converged {int(ok_d.sum())} / {int(ok_t.sum())} / reference {int(t['ok'].sum())}")
-    assert n_d == 3 * 11 and n_t != n_d                     # (2 forward-mode launches + update) x (times + 1) rounds
+    assert n_d == 3 * 11 + 1 and n_t != n_d                 # bone matrices + (2 forward-mode launches + update) x (times + 1) rounds
     for ps, ok in ((ps_d, ok_d),):
         agree = (ok == t["ok"]).float().mean().item()
         both = ok & t["ok"]
