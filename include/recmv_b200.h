@@ -150,6 +150,11 @@ RECMV_API int recmv_sdf_pack_weights(const float* W_all, const float* b_all, voi
  * NULL.                                                                                           */
 RECMV_API int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float* pe_w /*host*/,
                       float* out_sdf, float* out_feat, int64_t P, int mode, recmv_stream_t stream);
+/* the same with the point count read from DEVICE memory: *count_dev points (clamped to `capacity`, for which the launch
+ * is sized) -- consumer of device-built worklists (recmv_c2f_compact).  TC modes only.                             */
+RECMV_API int recmv_sdf_mlp_fwd_counted(const float* x, const void* packed, const float* pe_w /*host*/, float* out_sdf,
+                              float* out_feat, int64_t capacity, const int* count_dev, int mode,
+                              recmv_stream_t stream);
 
 /* ---- A2/A3 training path: what `loss.backward()` (train.py:325) runs through model/network.py:89-119 ---------
  * (and through Deformer.py:171-206 / RenderNet.py:59-96 -- the entry points below are generic over the layer list).
@@ -256,6 +261,29 @@ RECMV_API int recmv_interp2x_boundary3d_bwd(const float* grad_output, float* gra
                                   int W, recmv_stream_t stream);
 RECMV_API int recmv_c2f_todo_mask(const uint8_t* is_boundary, const uint8_t* done, uint8_t* todo, int D, int H,
                         int W, recmv_stream_t stream);
+
+/* ---- A11 / (f2): the sweep of one pyramid level as a DEVICE WORKLIST (SURVEY 8b `recmv_c2f_sweep`) -----------------
+ * replaces the coordinate-list bookkeeping of MCAcc/seg3d_lossless.py:306-428 (nonzero / unique / index scatter, a
+ * host sync per step).  level / final_res are (W, H, D) = (x, y, z) lattice sizes (host).
+ *  recmv_c2f_done_up      : done_up[2z,2y,2x] = done[z,y,x], 0 elsewhere.
+ *  recmv_c2f_compact      : voxels with todo != 0 -> idx_out[i] (flat level index), points_out[i] = the query point of
+ *                           batch_eval (:89-100), bit-identical arithmetic; counters (device int32[2] = {count, overflow},
+ *                           zeroed by the caller) is advanced with one atomic per warp; order is unspecified.
+ *  recmv_sdf_mlp_fwd_counted (above): evaluates points_out[0 .. *counters) without the host knowing the count.
+ *  recmv_c2f_scatter      : occ[idx] = vals, done[idx] = 1, calculated[final-lattice position] = 1; a sign flip against
+ *                           the interpolated value sets conflict_flag[idx] (caller zeroes it); stats (device int32[2])
+ *                           += {queried, conflicts}.
+ *  recmv_c2f_conflict_todo: todo = dilate3x3x3(conflict_flag) & ~calculated[z*sz, y*sy, x*sx]  (:392-420).          */
+RECMV_API int recmv_c2f_done_up(const uint8_t* done, int D, int H, int W, uint8_t* done_up, recmv_stream_t stream);
+RECMV_API int recmv_c2f_compact(const uint8_t* todo, const int level[3] /*host*/, const int final_res[3] /*host*/,
+                      const float b_min[3] /*host*/, const float b_max[3] /*host*/, int32_t* idx_out, float* points_out,
+                      int32_t* counters, int capacity, recmv_stream_t stream);
+RECMV_API int recmv_c2f_scatter(const int32_t* idx, const float* vals, const int32_t* counters, int capacity,
+                      const int level[3] /*host*/, const int final_res[3] /*host*/, float* occ, uint8_t* done,
+                      uint8_t* calculated, uint8_t* conflict_flag, float balance_value, int32_t* stats,
+                      recmv_stream_t stream);
+RECMV_API int recmv_c2f_conflict_todo(const uint8_t* conflict_flag, const uint8_t* calculated, const int level[3] /*host*/,
+                            const int final_res[3] /*host*/, uint8_t* todo, recmv_stream_t stream);
 
 /* ---- A10: surface-point solve of a batch of rays on the device (utils/FindSurfacePs.py:145-353) -------------------
  * ps [P,3]: in = seeds (FindSurfacePs), out = solution; ok [P] = converged (|f| < dthreshold and the angle between

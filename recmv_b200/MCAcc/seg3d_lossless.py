@@ -99,7 +99,76 @@ class Seg3dLossless(nn.Module):
         flat[idx] = vals
         return idx, interp, vals
 
+    # ---- device-worklist sweep ------------------------------------------------------------------------------------
+    def _device_net(self):
+        """(sdf_net, ratio) when `query_func` declares itself as a recmv_b200 ImplicitNetwork evaluated under no_grad
+        (attribute `recmv_sdf`, set by recmv_b200.discretize / INTEGRATION.md) and the tcgen05 engine can run it."""
+        tag = getattr(self.query_func, "recmv_sdf", None)
+        if tag is None or not self.b_min.is_cuda:
+            return None
+        net, ratio = tag
+        from .. import ops
+        mode = ops.DEFAULT_MLP_MODE if net.mlp_mode is None else net.mlp_mode
+        if not getattr(net, "_fusable", False) or mode == ops.MLP_FP32_SIMT:
+            return None
+        return net, ratio, mode
+
+    def _forward_device(self, net, ratio, mode):
+        """Same sweep, same voxels re-queried, same arithmetic for the query points -- as a device worklist: per level
+        ONE host read (statistics / overflow / "were there conflicts left"), no nonzero / unique / index scatter.
+        The grid equals the torch-op path's bit for bit (tests/test_gpu_surface.py)."""
+        from .. import ops
+        dev = self.b_min.device
+        final = self.resolutions[-1]
+        Wf, Hf, Df = (int(v) for v in final)
+        b_min, b_max = self.b_min.view(-1).tolist(), self.b_max.view(-1).tolist()
+        packed, pe_w = net.packed_weights(), net._pe_weights(ratio)
+        calculated = torch.zeros((Df, Hf, Wf), dtype=torch.uint8, device=dev)
+        stats = torch.zeros((2,), dtype=torch.int32, device=dev)
+        self.stats = []
+        occ, done = None, None
+        for li, res in enumerate(self.resolutions):
+            W, H, D = (int(v) for v in res)
+            stride = [(Wf - 1) // max(W - 1, 1), (Hf - 1) // max(H - 1, 1), (Df - 1) // max(D - 1, 1)]
+            if li == 0:
+                coords = create_grid3D(0, final.to(dev) - 1, steps=res.to(dev), device=dev).contiguous()
+                with torch.no_grad():
+                    occ = self.batch_eval(coords.unsqueeze(0)).view(1, 1, D, H, W).float().contiguous()
+                done = torch.ones((D, H, W), dtype=torch.uint8, device=dev)
+                calculated[::stride[2], ::stride[1], ::stride[0]] = 1
+                self.stats.append((W, H, D, D * H * W))
+                continue
+            occ, boundary = ops.interp2x_boundary3d_forward(occ, self.balance_value, 0 if self.use_cuda_impl else 1)
+            done = ops.c2f_done_up(done)
+            todo = ops.c2f_todo_mask(boundary[0, 0], done.view(torch.bool)).view(torch.uint8)
+            total = D * H * W
+            lvl = ops.C2fLevel((W, H, D), (Wf, Hf, Df), b_min, b_max, dev, total if total <= (1 << 22) else total // 4)
+            cflag = torch.empty((D, H, W), dtype=torch.uint8, device=dev)
+            stats.zero_()
+            lvl.query(todo, packed, pe_w, mode, occ, done, calculated, cflag, self.balance_value, stats)
+            while True:
+                for _ in range(2):      # conflict rounds, queued speculatively (an empty worklist costs a few no-op launches)
+                    lvl.conflict_todo(cflag, calculated, todo)
+                    lvl.query(todo, packed, pe_w, mode, occ, done, calculated, cflag, self.balance_value, stats)
+                # the level's one host synchronisation: {queried, conflicts of the last round, count, overflow}
+                queried, conflicts, _, overflow = (int(v) for v in torch.cat([stats, lvl.counters]).tolist())
+                if overflow:
+                    return None                                              # worklist overflow: caller falls back
+                if conflicts == 0:
+                    break
+            self.stats.append((W, H, D, queried))
+        self.last_sweep_path = "device-worklist"
+        return occ
+
     def forward(self, **kwargs):
+        devnet = self._device_net() if not kwargs else None
+        if devnet is not None and not torch.is_grad_enabled():
+            out = self._forward_device(*devnet)
+            if out is not None:
+                return out
+        return self._forward_torch(**kwargs)
+
+    def _forward_torch(self, **kwargs):
         dev = self.b_min.device
         final = self.resolutions[-1].to(dev)
         Wf, Hf, Df = (int(v) for v in final)

@@ -94,6 +94,14 @@ SIGNATURES = {
                                               c_void_p]),
     "recmv_interp2x_boundary3d_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "recmv_c2f_todo_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "recmv_c2f_done_up": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "recmv_c2f_compact": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_float), POINTER(c_float), c_void_p,
+                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "recmv_c2f_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "recmv_c2f_conflict_todo": (c_int, [c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p]),
+    "recmv_sdf_mlp_fwd_counted": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int64, c_void_p, c_int,
+                                          c_void_p]),
     "recmv_surface_solve_workspace": (c_size_t, [c_int64]),
     "recmv_surface_solve": (c_int, [POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p,
                                     POINTER(c_float), c_void_p, c_int, c_void_p, c_void_p, POINTER(Voxel), c_float, c_float,

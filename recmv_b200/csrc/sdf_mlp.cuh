@@ -55,7 +55,7 @@ constexpr float kInvalidSdf = 1e10f;
 int simt_sdf_forward(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
                      float* out_feat, int64_t P, cudaStream_t st);
 int tc_sdf_forward(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
-                   float* out_feat, int64_t P, int passes, cudaStream_t st);
+                   float* out_feat, int64_t P, int passes, cudaStream_t st, const int* P_dev = nullptr);
 
 // the per-device status record (mapped pinned host memory) the tcgen05 kernels report into: bounded-wait
 // time-outs (code 1) and fp16 operand-range violations (code 2); see recmv_check_async_errors

@@ -310,6 +310,24 @@ extern "C" int recmv_sdf_mlp_fwd(const float* x, const void* packed, const float
   return run_forward(src, packed, pe_w, out_sdf, out_feat, P, mode, (cudaStream_t)stream);
 }
 
+// Same as recmv_sdf_mlp_fwd with the number of points read from DEVICE memory (*count_dev, clamped to `capacity`): the
+// consumer of a device-built worklist (coarse-to-fine sweep) launches without a host round trip.
+extern "C" int recmv_sdf_mlp_fwd_counted(const float* x, const void* packed, const float* pe_w, float* out_sdf,
+                                         float* out_feat, int64_t capacity, const int* count_dev, int mode,
+                                         recmv_stream_t stream) {
+  if (capacity < 0) return RECMV_E_SHAPE;
+  if (capacity == 0) return RECMV_OK;
+  if (!x || !packed || !pe_w || !out_sdf || !count_dev) return RECMV_E_NULL;
+  if (mode != RECMV_MLP_TC_F16X3 && mode != RECMV_MLP_TC_F16X1) return RECMV_E_UNSUPPORTED;
+  PointSource src = {};
+  src.x = x;
+  src.S = 1;
+  PeWeights pw;
+  for (int i = 0; i < 12; ++i) pw.w[i] = pe_w[i];
+  return tc_sdf_forward(src, packed, pw, out_sdf, out_feat, capacity, mode == RECMV_MLP_TC_F16X3 ? 3 : 1,
+                        (cudaStream_t)stream, count_dev);
+}
+
 extern "C" int recmv_sdf_mlp_fwd_grad(const float* x, const void* packed, const float* pe_w, float* out_sdf,
                                       float* out_feat, float* out_grad, int64_t P, int mode,
                                       recmv_stream_t stream) {

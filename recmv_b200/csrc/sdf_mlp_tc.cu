@@ -81,6 +81,7 @@ struct TcParams {
   float* out_sdf;
   float* out_feat;
   long long P;
+  const int* P_dev;   // optional: actual point count in device memory (<= P)
   int passes;
   float acc_gain_kb;  // relative accumulator gain per 64-wide K block of a layer (4 accumulating MMAs)
   DevStatus* status;
@@ -231,7 +232,10 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
   const uint32_t lrank = crank & ~1u;             // cluster rank of this pair's leader
   const bool leader = rank == 0;
   constexpr int kPtsPerTile = kJvp ? 32 : 128;  // JVP: rows = 4 per point (value, d/dx, d/dy, d/dz)
-  const long long num_tiles = (prm.P + kPtsPerTile - 1) / kPtsPerTile;
+  // number of points: by value, or -- device worklists (coarse-to-fine sweep) -- read from device memory, bounded by
+  // the capacity prm.P the grid was sized for
+  const long long Ptot = prm.P_dev ? (long long)min((long long)max(__ldg(prm.P_dev), 0), prm.P) : prm.P;
+  const long long num_tiles = (Ptot + kPtsPerTile - 1) / kPtsPerTile;
   const long long cluster_id = blockIdx.x / (2 * kPairs), num_clusters = gridDim.x / (2 * kPairs);
   // every pair of a cluster iterates the same number of times (they consume the multicast weight stream
   // in lockstep); iterations past the last tile run on zero rows and write nothing
@@ -567,7 +571,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
             }
             if (kNet == 2) {
               // colour network: columns 0..2 of the tail tile -> tanh
-              if (p < prm.P && half == 0 && c0 == 0) {
+              if (p < Ptot && half == 0 && c0 == 0) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
                   prm.out_rgb[3 * p + c] = tanhf(fmaf(__uint_as_float(r[c]), acc_unscale, __ldg(bias + c)));
@@ -584,7 +588,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
 #pragma unroll
                     for (int j = 0; j < 3; ++j) dt[3 * c + j] = __shfl_sync(0xffffffffu, own, (lane & ~3) + 1 + j);
                   }
-                  if (is_value && p < prm.P) {
+                  if (is_value && p < Ptot) {
                     const float x = __ldg(prm.src.x + 3 * p), y = __ldg(prm.src.x + 3 * p + 1), z = __ldg(prm.src.x + 3 * p + 2);
                     const float tx = x + dv[0], ty = y + dv[1], tz = z + dv[2];
                     dt[0] += 1.f; dt[4] += 1.f; dt[8] += 1.f;   // d (p + offset) / d p
@@ -608,7 +612,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                     }
                   }
                 }
-              } else if (p < prm.P && half == 0 && c0 == 0) {
+              } else if (p < Ptot && half == 0 && c0 == 0) {
                 const float dx = fmaf(__uint_as_float(r[0]), acc_unscale, __ldg(bias + 0));
                 const float dy = fmaf(__uint_as_float(r[1]), acc_unscale, __ldg(bias + 1));
                 const float dz = fmaf(__uint_as_float(r[2]), acc_unscale, __ldg(bias + 2));
@@ -628,7 +632,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
                   prm.out_posed[3 * p + 2] = (T[8] * tx + T[9] * ty + T[10] * tz + T[11]) + __ldg(tr + 2);
                 }
               }
-            } else if (p < prm.P) {
+            } else if (p < Ptot) {
               // last layer: column 0 = sdf, columns 1..256 = features
               const bool ok = valid[(it & 1) * 64 + row] != 0;
               if (kJvp && !is_value) {
@@ -667,7 +671,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         float head[40];   // [p 3 | PE4(v) 27 | n 3 | feat 0..6]
 #pragma unroll
         for (int e = 0; e < 40; ++e) head[e] = 0.f;
-        const bool live = p < prm.P;
+        const bool live = p < Ptot;
         const float* ft = prm.feats + (size_t)(live ? p : 0) * 256;
         if (live) {
           float pe[39];
@@ -713,7 +717,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         float head[40];
 #pragma unroll
         for (int e = 0; e < 40; ++e) head[e] = 0.f;
-        const bool live = p < prm.P;
+        const bool live = p < Ptot;
         const bool value_row = !kJvp || (row & 3) == 0;
         const float* cond = prm.conds;
         if (live) {
@@ -757,7 +761,7 @@ sdf_tc_kernel(const __grid_constant__ CUtensorMap tmap128, const TcParams prm) {
         }
       } else {
       float pe[40];
-      if (p < prm.P) {
+      if (p < Ptot) {
         float cx, cy, cz;
         ok = fetch_point(prm.src, p, cx, cy, cz);
         if (!kJvp || (row & 3) == 0) {
@@ -876,7 +880,7 @@ int tc_max_clusters(int dev) {
 
 static int launch_tc(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
                      float* out_feat, float* out_grad, int64_t P, int passes, int dbg_layer, float* dbg_out, int* status_host,
-                     unsigned long long* trace, cudaStream_t st) {
+                     unsigned long long* trace, cudaStream_t st, const int* P_dev = nullptr) {
   if (passes != 1 && passes != 3) return RECMV_E_DTYPE;
   PackedLayout L = packed_layout();
   const char* pb = (const char*)packed;
@@ -901,7 +905,7 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
   TcParams prm = {};
   prm.src = src; prm.pw = pw;
   prm.bias = (const float*)(pb + L.bias_all_off);
-  prm.out_sdf = out_sdf; prm.out_feat = out_feat; prm.P = P; prm.passes = passes; prm.status = sd;
+  prm.out_sdf = out_sdf; prm.out_feat = out_feat; prm.P = P; prm.P_dev = P_dev; prm.passes = passes; prm.status = sd;
   set_acc_scales(prm);
   prm.dbg_layer = dbg_layer; prm.dbg_out = dbg_out; prm.trace = trace; prm.out_grad = out_grad;
   const int pts_per_tile = out_grad ? 32 : 128;
@@ -925,8 +929,8 @@ static int launch_tc(const PointSource& src, const void* packed, const PeWeights
 }
 
 int tc_sdf_forward(const PointSource& src, const void* packed, const PeWeights& pw, float* out_sdf,
-                   float* out_feat, int64_t P, int passes, cudaStream_t st) {
-  return launch_tc(src, packed, pw, out_sdf, out_feat, nullptr, P, passes, -1, nullptr, nullptr, nullptr, st);
+                   float* out_feat, int64_t P, int passes, cudaStream_t st, const int* P_dev) {
+  return launch_tc(src, packed, pw, out_sdf, out_feat, nullptr, P, passes, -1, nullptr, nullptr, nullptr, st, P_dev);
 }
 
 int tc_sdf_forward_grad(const float* x, const void* packed, const PeWeights& pw, float* out_sdf, float* out_feat,

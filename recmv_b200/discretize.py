@@ -11,9 +11,13 @@ def discretize_sdf(sdf_net, engine, ratio, balance_value=0.):
     def query_func(points):
         with torch.no_grad():   # fused no-grad forward: one launch per query batch
             return sdf_net.forward(points.reshape(-1, 3), ratio).reshape(1, 1, -1)
+    # declares the query as "this recmv_b200 network under no_grad": the sweep may then run as a device worklist
+    # (Seg3dLossless._forward_device); any other query function takes the torch-op path
+    query_func.recmv_sdf = (sdf_net, ratio)
     engine.balance_value = balance_value
     engine.query_func = query_func
-    sdfs = engine.forward()
+    with torch.no_grad():
+        sdfs = engine.forward()
     verts, faces = ops.mc_gpu(sdfs[0, 0].permute(2, 1, 0).contiguous(), engine.spacing_x, engine.spacing_y,
                               engine.spacing_z, engine.bx, engine.by, engine.bz, balance_value)
     return verts, faces

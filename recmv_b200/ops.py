@@ -795,6 +795,52 @@ def c2f_todo_mask(is_boundary, done):
     return todo.view(torch.bool)
 
 
+class C2fLevel:
+    """Device worklist of one pyramid level (recmv_c2f_*): todo mask -> (index, point) list -> fused SDF launch with a
+    device-side count -> scatter + conflict flags; no host round trip inside a round."""
+
+    def __init__(self, level_whd, final_whd, b_min, b_max, device, capacity):
+        self.level = (ctypes.c_int * 3)(*[int(v) for v in level_whd])
+        self.final = (ctypes.c_int * 3)(*[int(v) for v in final_whd])
+        self.bmin = (c_float * 3)(*[float(v) for v in b_min])
+        self.bmax = (c_float * 3)(*[float(v) for v in b_max])
+        self.cap = int(capacity)
+        self.dev = device
+        self.idx = torch.empty((self.cap,), dtype=torch.int32, device=device)
+        self.pts = torch.empty((self.cap, 3), dtype=torch.float32, device=device)
+        self.vals = torch.empty((self.cap, 1), dtype=torch.float32, device=device)
+        self.counters = torch.zeros((2,), dtype=torch.int32, device=device)    # count, overflow
+
+    def query(self, todo_u8, packed, pe_w, mode, occ, done_u8, calculated_u8, cflag_u8, balance, stats):
+        lib = _lib.load()
+        with torch.cuda.device(self.dev):
+            st = _stream(occ)
+            self.counters[0:1].zero_()          # overflow is sticky for the level
+            check(lib.recmv_c2f_compact(_ptr(todo_u8), self.level, self.final, self.bmin, self.bmax, _ptr(self.idx),
+                                        _ptr(self.pts), _ptr(self.counters), self.cap, st), "recmv_c2f_compact")
+            check(lib.recmv_sdf_mlp_fwd_counted(_ptr(self.pts), _ptr(packed), _pe_array(pe_w), _ptr(self.vals), None,
+                                                self.cap, _ptr(self.counters), mode, st), "recmv_sdf_mlp_fwd_counted")
+            cflag_u8.zero_()
+            stats[1:2].zero_()                  # conflicts of THIS round
+            check(lib.recmv_c2f_scatter(_ptr(self.idx), _ptr(self.vals), _ptr(self.counters), self.cap, self.level,
+                                        self.final, _ptr(occ), _ptr(done_u8), _ptr(calculated_u8), _ptr(cflag_u8),
+                                        float(balance), _ptr(stats), st), "recmv_c2f_scatter")
+
+    def conflict_todo(self, cflag_u8, calculated_u8, todo_u8):
+        with torch.cuda.device(self.dev):
+            check(_lib.load().recmv_c2f_conflict_todo(_ptr(cflag_u8), _ptr(calculated_u8), self.level, self.final,
+                                                      _ptr(todo_u8), _stream(todo_u8)), "recmv_c2f_conflict_todo")
+        return todo_u8
+
+
+def c2f_done_up(done_u8):
+    D, H, W = done_u8.shape
+    up = torch.empty((2 * D - 1, 2 * H - 1, 2 * W - 1), dtype=torch.uint8, device=done_u8.device)
+    with torch.cuda.device(up.device):
+        check(_lib.load().recmv_c2f_done_up(_ptr(done_u8), D, H, W, _ptr(up), _stream(up)), "recmv_c2f_done_up")
+    return up
+
+
 def surface_solve(cam_pos, rays, seeds, batch_inds, sdf_packed, sdf_pe_w, tr_packed, tr_pe_w, conds, skin, dthreshold,
                   athreshold, w1, w2, times, mode=None):
     """Device-resident surface solve (recmv_surface_solve).  skin = (A, trans, ws_cl, center, extend).

@@ -103,6 +103,34 @@ def test_c2f_sweep_and_discretize_on_gpu():
     assert sum(s[3] for s in eng2.stats) < 0.25 * 129 ** 3
 
 
+@pytest.mark.parametrize("resolutions", [[17, 33, 65, 129], [(15, 21, 9), (29, 41, 17), (57, 81, 33), (113, 161, 65)]])
+def test_c2f_device_worklist_is_bit_identical_to_the_torch_path(resolutions):
+    """Seg3dLossless with the sweep as a device worklist (recmv_c2f_compact / recmv_sdf_mlp_fwd_counted /
+    recmv_c2f_scatter / recmv_c2f_conflict_todo): same voxels re-queried, same query-point arithmetic -> the grid equals
+    the torch-op path's (itself bit-identical to the reference class, tests/test_c2f_cpu.py) bit for bit, per-level
+    statistics included; isotropic pyramid and the anisotropic 'coarse' pyramid of train.py:42-48 (halved)."""
+    from recmv_b200 import testing
+    sdf = testing.build_sdf(M.getTmpSdf, seed=0, perturb_seed=101).to(DEV)
+    eng = Seg3dLossless(None, b_min=[-1, -1, -1], b_max=[1, 1, 1], resolutions=resolutions, align_corners=False,
+                        balance_value=0.0).to(DEV)
+
+    def q(points):
+        with torch.no_grad():
+            return sdf.forward(points.reshape(-1, 3), 0.8).reshape(1, 1, -1)
+    eng.query_func = q
+    with torch.no_grad():
+        g_torch = eng.forward().clone()
+    assert eng.last_sweep_path == "fused"
+    st_torch = list(eng.stats)
+    q.recmv_sdf = (sdf, 0.8)
+    with torch.no_grad():
+        g_dev = eng.forward()
+    assert eng.last_sweep_path == "device-worklist"
+    assert torch.equal(g_dev, g_torch)
+    assert list(eng.stats) == st_torch
+    ops.check_async_errors()
+
+
 def test_fused_translator_and_deformer_match_reference():
     """A4 / A5: MLPTranslator alone (golden from the reference class) and the CompositeDeformer = translator +
     LBS in one launch (golden `ds` from the reference CompositeDeformer)."""
