@@ -262,6 +262,21 @@ RECMV_API int recmv_interp2x_boundary3d_bwd(const float* grad_output, float* gra
 RECMV_API int recmv_c2f_todo_mask(const uint8_t* is_boundary, const uint8_t* done, uint8_t* todo, int D, int H,
                         int W, recmv_stream_t stream);
 
+/* ---- A9 + (f3): FindSurfacePs + view_rays + the mask filter of sample_train_ray ------------------------------------
+ * replaces utils/FindSurfacePs.py:7-60 (nonzero / torch_scatter scatter(min) / gathers), model/CameraMine.py:146-167
+ * (view_rays) and the `gt_mask > 0` selection of OptimGarmentNetwork.py:1006-1011, in three launches and one ordered
+ * compaction.  pix_to_face [N,H,W,K] int64, bary [N,H,W,K,3] f32 (pytorch3d Fragments), verts [V,3], faces [F,3] int64,
+ * mask [N,H,W] f32 or NULL, camera = host float[13] {fx, fy, px, py, R row-major} or NULL.
+ * Outputs have capacity N*H*W rows and are filled in (n, row, col) order -- the order of the reference's `nonzero`:
+ * out_batch/out_row/out_col/out_finds int64, out_pts [.,3] (barycentric seed point on the canonical mesh), out_rays [.,3]
+ * (only with a camera).  counters (device int32[1]) <- number of rows.  scratch: recmv_fragment_decode_scratch_bytes.   */
+RECMV_API size_t recmv_fragment_decode_scratch_bytes(int64_t npix);
+RECMV_API int recmv_fragment_decode(const int64_t* pix_to_face, const float* bary, int N, int H, int W, int K,
+                          const float* verts, const int64_t* faces, int64_t num_faces, const float* mask,
+                          const float* camera /*host[13]*/, void* scratch, int64_t* out_batch, int64_t* out_row,
+                          int64_t* out_col, float* out_pts, int64_t* out_finds, float* out_rays, int32_t* counters,
+                          recmv_stream_t stream);
+
 /* ---- A11 / (f2): the sweep of one pyramid level as a DEVICE WORKLIST (SURVEY 8b `recmv_c2f_sweep`) -----------------
  * replaces the coordinate-list bookkeeping of MCAcc/seg3d_lossless.py:306-428 (nonzero / unique / index scatter, a
  * host sync per step).  level / final_res are (W, H, D) = (x, y, z) lattice sizes (host).

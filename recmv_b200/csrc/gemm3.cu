@@ -161,37 +161,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
     const float dyn = prm.dyn_scale ? __ldg(prm.dyn_scale) : 1.f;
     const float sa = T.a_scale * dyn, sb = T.b_scale;
     float colsum = 0.f;                        // EPI_ACCUM: sum over k of A[k][m0 + (t & 127)], unscaled
-    for (long long kb = 0; kb < nkb; ++kb) {
-      const int s = (int)(kb % kStages);
-      const uint32_t par = (uint32_t)((kb / kStages) & 1);
-      mbar_wait(BAR(kBarEmpty + s), par ^ 1u, abort_flag, prm.status, 2000 + s);
-      const uint32_t st = base + (uint32_t)s * kStageBytes;
+    // Task geometry of this thread (4 tasks of 8 K-consecutive elements per operand and K block):
+    //   transposed read: row r = t & 127, chunks c = (t >> 7) + 2 i  -- lanes walk consecutive rows (coalesced)
+    //   direct read    : chunk c = t & 7, rows r = (t >> 3) + 32 i   -- 8 lanes cover one row's 64 floats
+    // ALL loads of a K block are issued before any of them is consumed, and the loads of K block kb + 1 are issued
+    // right after K block kb has been written to shared memory: the global-load latency (~0.7 us, against 0.4 us of MMAs
+    // per K block) overlaps the slot wait and the other warps' conversions instead of serialising 8 round trips.
+    float va[4][8], vb[4][8];
+    auto load_block = [&](long long kb) {
       const long long k0 = kb * kBK;
-      // ---- A tile ----
       if (T.a_transposed) {
         const int r = t & 127;
         const bool rok = m0 + r < T.M;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = (t >> 7) + 2 * i;
-          float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const long long k = k0 + c * 8 + j;
-            v[j] = (rok && k < T.K) ? __ldg(T.A + k * T.lda + (m0 + r)) : 0.f;
+            va[i][j] = (rok && k < T.K) ? __ldg(T.A + k * T.lda + (m0 + r)) : 0.f;
           }
-          if (T.colsum) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) colsum += v[j];
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= sa;
-          range_check8(v, prm.status, 2300);
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          const uint32_t off = sw128_offset(r, c);
-          st_shared_v4(st + off, hi);
-          st_shared_v4(st + kPlane + off, lo);
         }
       } else {
         const int c = t & 7;
@@ -199,45 +188,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         for (int i = 0; i < 4; ++i) {
           const int r = (t >> 3) + 32 * i;
           const long long k = k0 + c * 8;
-          float v[8];
           const bool rok = m0 + r < T.M;
           const float* src = T.A + (long long)(m0 + r) * T.lda + k;
           if (rok && k + 8 <= T.K && ((T.lda & 3) == 0)) {
             const float4 x0 = __ldg(reinterpret_cast<const float4*>(src)), x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+            va[i][0] = x0.x; va[i][1] = x0.y; va[i][2] = x0.z; va[i][3] = x0.w;
+            va[i][4] = x1.x; va[i][5] = x1.y; va[i][6] = x1.z; va[i][7] = x1.w;
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (rok && k + j < T.K) ? __ldg(src + j) : 0.f;
+            for (int j = 0; j < 8; ++j) va[i][j] = (rok && k + j < T.K) ? __ldg(src + j) : 0.f;
           }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= sa;
-          range_check8(v, prm.status, 2301);
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          const uint32_t off = sw128_offset(r, c);
-          st_shared_v4(st + off, hi);
-          st_shared_v4(st + kPlane + off, lo);
         }
       }
-      // ---- B tile ----
       if (T.b_transposed) {
         const int r = t & 127;
         const bool rok = n0 + r < T.N;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = (t >> 7) + 2 * i;
-          float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const long long k = k0 + c * 8 + j;
-            v[j] = (rok && k < T.K) ? __ldg(T.B + k * T.ldb + (n0 + r)) * sb : 0.f;
+            vb[i][j] = (rok && k < T.K) ? __ldg(T.B + k * T.ldb + (n0 + r)) : 0.f;
           }
-          range_check8(v, prm.status, 2302);
-          uint4 hi, lo;
-          split8(v, hi, lo);
-          const uint32_t off = sw128_offset(r, c);
-          st_shared_v4(st + 2 * kPlane + off, hi);
-          st_shared_v4(st + 3 * kPlane + off, lo);
         }
       } else {
         const int c = t & 7;
@@ -245,21 +218,53 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
         for (int i = 0; i < 4; ++i) {
           const int r = (t >> 3) + 32 * i;
           const long long k = k0 + c * 8;
-          float v[8];
           const bool rok = n0 + r < T.N;
           const float* src = T.B + (long long)(n0 + r) * T.ldb + k;
           if (rok && k + 8 <= T.K && ((T.ldb & 3) == 0)) {
             const float4 x0 = __ldg(reinterpret_cast<const float4*>(src)), x1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+            vb[i][0] = x0.x; vb[i][1] = x0.y; vb[i][2] = x0.z; vb[i][3] = x0.w;
+            vb[i][4] = x1.x; vb[i][5] = x1.y; vb[i][6] = x1.z; vb[i][7] = x1.w;
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (rok && k + j < T.K) ? __ldg(src + j) : 0.f;
+            for (int j = 0; j < 8; ++j) vb[i][j] = (rok && k + j < T.K) ? __ldg(src + j) : 0.f;
+          }
+        }
+      }
+    };
+    if (nkb > 0) load_block(0);
+    for (long long kb = 0; kb < nkb; ++kb) {
+      const int s = (int)(kb % kStages);
+      const uint32_t par = (uint32_t)((kb / kStages) & 1);
+      mbar_wait(BAR(kBarEmpty + s), par ^ 1u, abort_flag, prm.status, 2000 + s);
+      const uint32_t st = base + (uint32_t)s * kStageBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // ---- A ----
+        {
+          const int r = T.a_transposed ? (t & 127) : (t >> 3) + 32 * i;
+          const int c = T.a_transposed ? (t >> 7) + 2 * i : (t & 7);
+          if (T.colsum) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) colsum += va[i][j];
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= sb;
-          range_check8(v, prm.status, 2303);
+          for (int j = 0; j < 8; ++j) va[i][j] *= sa;
+          range_check8(va[i], prm.status, 2300);
           uint4 hi, lo;
-          split8(v, hi, lo);
+          split8(va[i], hi, lo);
+          const uint32_t off = sw128_offset(r, c);
+          st_shared_v4(st + off, hi);
+          st_shared_v4(st + kPlane + off, lo);
+        }
+        // ---- B ----
+        {
+          const int r = T.b_transposed ? (t & 127) : (t >> 3) + 32 * i;
+          const int c = T.b_transposed ? (t >> 7) + 2 * i : (t & 7);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vb[i][j] *= sb;
+          range_check8(vb[i], prm.status, 2302);
+          uint4 hi, lo;
+          split8(vb[i], hi, lo);
           const uint32_t off = sw128_offset(r, c);
           st_shared_v4(st + 2 * kPlane + off, hi);
           st_shared_v4(st + 3 * kPlane + off, lo);
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive_local(BAR(kBarFull + s));
+      if (kb + 1 < nkb) load_block(kb + 1);
     }
     // bias gradient: two producer threads hold the two halves of every row's column sum (commutative: deterministic)
     if (T.colsum && tn == 0 && T.a_transposed && m0 + (t & 127) < T.M) atomicAdd(T.colsum + m0 + (t & 127), colsum);

@@ -208,20 +208,23 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_count_kernel(const unsigned* 
   if (lane == 0) block_sums[seg] = make_int2(tot & 0xffff, tot >> 16);
 }
 
-// totals[0] = V, totals[1] = F, totals[2] = overflow flag (set by the emit passes), totals[3] = 0
+// totals[0] = V, totals[1] = F, totals[2] = overflow flag (set by the emit passes), totals[3] = 0.
+// One CTA, one pass: every thread owns a contiguous run of ceil(nb / 1024) segment sums (serial), the 1024 run totals
+// are scanned once across the CTA, and the run is rewritten as exclusive prefixes.
 __global__ void __launch_bounds__(kMcThreads) mc_scan_kernel(int2* __restrict__ block_sums, int nb,
                                                              int* __restrict__ totals) {
   __shared__ int2 tot;
-  int2 carry = make_int2(0, 0);
-  for (int base = 0; base < nb; base += kMcThreads) {
-    int b = base + threadIdx.x;
-    int2 v = b < nb ? block_sums[b] : make_int2(0, 0);
-    int2 ex = block_excl_scan(v, &tot);
-    if (b < nb) block_sums[b] = make_int2(ex.x + carry.x, ex.y + carry.y);
-    carry.x += tot.x; carry.y += tot.y;
-    __syncthreads();
+  const int per = (nb + kMcThreads - 1) / kMcThreads;
+  const int b0 = threadIdx.x * per, b1 = min(b0 + per, nb);
+  int2 mine = make_int2(0, 0);
+  for (int b = b0; b < b1; ++b) { const int2 v = block_sums[b]; mine.x += v.x; mine.y += v.y; }
+  int2 run = block_excl_scan(mine, &tot);
+  for (int b = b0; b < b1; ++b) {
+    const int2 v = block_sums[b];
+    block_sums[b] = run;
+    run.x += v.x; run.y += v.y;
   }
-  if (threadIdx.x == 0) { totals[0] = carry.x; totals[1] = carry.y; totals[2] = 0; totals[3] = 0; }
+  if (threadIdx.x == 0) { totals[0] = tot.x; totals[1] = tot.y; totals[2] = 0; totals[3] = 0; }
 }
 
 // (iso - v1) / (v2 - v1) evaluated like d_fGetOffset (CudaKernels.cu:304-314): float differences,

@@ -131,6 +131,7 @@ class MLPTranslator(nn.Module):
         self.relu = nn.ReLU()
         self.offset = {}
         self.mlp_mode = None
+        self.train_fused = True   # grad-enabled forwards go through ops.TranslatorTrainFunction (False: torch graph)
         self.last_path = None
         self._packed, self._packed_key = None, None
         self.fusable = (multires == 6 and feature_vector_size == 128 and not weight_norm)
@@ -161,6 +162,22 @@ class MLPTranslator(nn.Module):
                 return tr
             self.offset[offset_type] = off.view(ps.shape[0], ps.shape[1], 3)
             return tr.view(ps.shape[0], ps.shape[1], 3)
+        if (self.fusable and self.train_fused and ps.is_cuda and self.mlp_mode != ops.MLP_FP32_SIMT
+                and conds.dim() == 2):
+            # training path: tcgen05 layer GEMMs forward + backward (ops.TranslatorTrainFunction)
+            self.last_path = "fused-train"
+            flat = ps.reshape(-1, 3).contiguous().float()
+            inds = batch_inds if batch_inds is not None else torch.arange(
+                ps.shape[0], device=ps.device).repeat_interleave(ps.shape[1])
+            off = ops.TranslatorTrainFunction.apply(flat, conds.contiguous().float(), inds.contiguous().long(),
+                                                    ratio_to_weights(self.multires, ratio),
+                                                    *[getattr(self, "lin%d" % l).weight for l in range(5)],
+                                                    *[getattr(self, "lin%d" % l).bias for l in range(5)])
+            if batch_inds is not None:
+                self.offset[offset_type] = off
+                return flat + off
+            self.offset[offset_type] = off.view(ps.shape[0], ps.shape[1], 3)
+            return ps + off.view(ps.shape[0], ps.shape[1], 3)
         self.last_path = "autograd-composite"
         if self.embed_fn is not None:
             ps = self.embed_fn(ps, ratio_to_weights(self.multires, ratio))

@@ -35,6 +35,7 @@ class RenderingNetwork_view_norm(nn.Module):
         self.relu = nn.ReLU()
         self.tanh = nn.Tanh()
         self.mlp_mode = None
+        self.train_fused = True   # grad-enabled forwards go through ops.RenderNetTrainFunction (False: torch graph)
         self.last_path = None
         self._packed, self._packed_key = None, None
         self.fusable = (mode == 'idr' and multires_v == 4 and multires_n == 0 and feature_vector_size == 256
@@ -67,6 +68,24 @@ class RenderingNetwork_view_norm(nn.Module):
             self.last_path = "fused"
             return ops.rendernet_forward(points, normals, view_dirs, feature_vectors, self.packed_weights(),
                                          ratio_to_weights(self.multires_v, ratio), self.mlp_mode)
+        if (self.fusable and self.train_fused and points.is_cuda and points.dim() == 2
+                and self.mlp_mode != ops.MLP_FP32_SIMT):
+            # training path: tcgen05 layer GEMMs forward + backward (ops.RenderNetTrainFunction); tanh and the
+            # weight-norm re-parametrisation stay (tiny) torch graphs
+            self.last_path = "fused-train"
+            Ws, bs = [], []
+            for l in range(self.num_layers - 1):
+                lin = getattr(self, "lin" + str(l))
+                if hasattr(lin, "weight_g"):
+                    v, g = lin.weight_v, lin.weight_g
+                    Ws.append(v * (g / v.norm(dim=1, keepdim=True)))
+                else:
+                    Ws.append(lin.weight)
+                bs.append(lin.bias)
+            pre = ops.RenderNetTrainFunction.apply(points.contiguous().float(), normals.contiguous().float(),
+                                                   view_dirs.contiguous().float(), feature_vectors.contiguous().float(),
+                                                   ratio_to_weights(self.multires_v, ratio), *Ws, *bs)
+            return self.tanh(pre)
         self.last_path = "autograd-composite"
         if self.embedv_fn is not None:
             view_dirs = self.embedv_fn(view_dirs, ratio_to_weights(self.multires_v, ratio))

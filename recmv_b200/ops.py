@@ -618,6 +618,151 @@ class SdfMlpTrainFunction(torch.autograd.Function):
         return (dx, None, None, None, *dW, *db)
 
 
+def _plain_mlp_forward(X0, Ws, bs):
+    """ReLU MLP on tcgen05 layer GEMMs: returns (output [P, out_last], saved layer inputs [X0, X1, ...])."""
+    P, dev = X0.shape[0], X0.device
+    Ws = [w.detach().contiguous().float() for w in Ws]
+    bs = [b.detach().contiguous().float() for b in bs]
+    acts = [X0]
+    n = len(Ws)
+    for l in range(n):
+        o, i = Ws[l].shape
+        last = l == n - 1
+        Y = torch.empty((P, o if not last else ((o + 3) // 4) * 4), dtype=torch.float32, device=dev)
+        mlp_fwd_layer(acts[l], Ws[l], bs[l], o, i, ACT_NONE if last else ACT_RELU, Y)
+        acts.append(Y)
+    return acts[-1][:, :Ws[-1].shape[0]], acts[:-1]
+
+
+def _plain_mlp_backward(g_out, Ws, acts, need_w, need_x0):
+    """g_out [P, out_last] -> (dX0 [P, in_0 padded] or None, dW list, db list) for the ReLU MLP."""
+    P, dev = g_out.shape[0], g_out.device
+    n = len(Ws)
+    o_last = Ws[-1].shape[0]
+    G = [None] * n
+    G[n - 1] = torch.zeros((P, ((o_last + 3) // 4) * 4), dtype=torch.float32, device=dev)
+    G[n - 1][:, :o_last] = g_out
+    dyn = grad_dyn_scale(G[n - 1])
+    for l in range(n - 1, 0, -1):
+        o, i = Ws[l].shape
+        G[l - 1] = torch.empty((P, i), dtype=torch.float32, device=dev)
+        mlp_bwd_data_layer(G[l], Ws[l], o, i, acts[l], ACT_RELU, G[l - 1], dyn_scale=dyn)
+    dX0 = None
+    if need_x0:
+        o, i = Ws[0].shape
+        dX0 = torch.empty((P, ((i + 3) // 4) * 4), dtype=torch.float32, device=dev)
+        mlp_bwd_data_layer(G[0], Ws[0], o, i, None, ACT_NONE, dX0, dyn_scale=dyn)
+    dW, db = [None] * n, [None] * n
+    if need_w:
+        dW, db = mlp_bwd_weight(G, list(acts), [w.shape[0] for w in Ws], [w.shape[1] for w in Ws], None, dyn)
+    return dX0, dW, db
+
+
+def _plain_composite(X0, Ws, bs):
+    h = X0
+    for l in range(len(Ws)):
+        h = torch.nn.functional.linear(h, Ws[l], bs[l])
+        if l < len(Ws) - 1:
+            h = torch.relu(h)
+    return h
+
+
+class TranslatorTrainFunction(torch.autograd.Function):
+    """MLPTranslator offset MLP with gradients (model/Deformer.py:171-206): input row [PE6(p) 39 | cond[frame] 128] ->
+    512 x4 ReLU -> 3, forward / backward-data / weight gradient on tcgen05 (csrc/gemm3.cu); returns the OFFSET (the caller
+    adds p).  create_graph=True falls back to a torch graph inside backward, like SdfMlpTrainFunction."""
+    last_backward = None
+
+    @staticmethod
+    def forward(ctx, ps, conds, batch_inds, pe_w, *Wb):
+        n = len(Wb) // 2
+        Ws, bs = Wb[:n], Wb[n:]
+        P, dev = ps.shape[0], ps.device
+        X0 = torch.zeros((P, 168), dtype=torch.float32, device=dev)
+        pe_forward(ps, pe_w, 6, X0)
+        X0[:, 39:167] = conds.detach()[batch_inds]
+        out, acts = _plain_mlp_forward(X0, Ws, bs)
+        ctx.pe_w, ctx.n = [float(w) for w in pe_w], n
+        ctx.save_for_backward(ps, conds, batch_inds, *Wb, *acts)
+        return out.contiguous()
+
+    @staticmethod
+    def backward(ctx, g_off):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        ps, conds, batch_inds = saved[:3]
+        Ws, bs, acts = saved[3:3 + n], saved[3 + n:3 + 2 * n], saved[3 + 2 * n:]
+        need = ctx.needs_input_grad
+        if torch.is_grad_enabled():
+            TranslatorTrainFunction.last_backward = "autograd-composite (create_graph)"
+            with torch.enable_grad():
+                x0 = torch.cat([_pe_torch(ps, ctx.pe_w, 6), conds[batch_inds]], 1)
+                out = _plain_composite(x0, Ws, bs)
+                ins = [t for t in [ps, conds] + list(Ws) + list(bs) if t.requires_grad]
+                gr = iter(torch.autograd.grad([out], ins, [g_off], create_graph=True, allow_unused=True))
+            res = [next(gr) if t.requires_grad else None for t in [ps, conds] + list(Ws) + list(bs)]
+            return (res[0], res[1], None, None, *res[2:])
+        TranslatorTrainFunction.last_backward = "fused-tcgen05"
+        dX0, dW, db = _plain_mlp_backward(g_off.contiguous().float(), Ws, acts, any(need[4:]), need[0] or need[1])
+        dps = dconds = None
+        if need[0]:
+            dps = pe_backward(ps, dX0, None, ctx.pe_w, 6)
+        if need[1]:
+            dconds = torch.zeros_like(conds).index_add_(0, batch_inds, dX0[:, 39:167])
+        return (dps, dconds, None, None, *dW, *db)
+
+
+class RenderNetTrainFunction(torch.autograd.Function):
+    """RenderingNetwork_view_norm ('idr', model/RenderNet.py:59-96) with gradients: input row [p 3 | PE4(v) 27 | n 3 |
+    feat 256] -> 512 x4 ReLU -> 3 (pre-tanh; the caller applies tanh), all GEMMs on tcgen05."""
+    last_backward = None
+
+    @staticmethod
+    def forward(ctx, points, normals, view_dirs, feats, pe_w, *Wb):
+        n = len(Wb) // 2
+        Ws, bs = Wb[:n], Wb[n:]
+        P, dev = points.shape[0], points.device
+        X0 = torch.zeros((P, 292), dtype=torch.float32, device=dev)
+        X0[:, 0:3] = points.detach()
+        pe_forward(view_dirs.detach().contiguous(), pe_w, 4, X0[:, 3:])
+        X0[:, 30:33] = normals.detach()
+        X0[:, 33:289] = feats.detach()
+        out, acts = _plain_mlp_forward(X0, Ws, bs)
+        ctx.pe_w, ctx.n = [float(w) for w in pe_w], n
+        ctx.save_for_backward(points, normals, view_dirs, feats, *Wb, *acts)
+        return out.contiguous()
+
+    @staticmethod
+    def backward(ctx, g_out):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        points, normals, view_dirs, feats = saved[:4]
+        Ws, bs, acts = saved[4:4 + n], saved[4 + n:4 + 2 * n], saved[4 + 2 * n:]
+        need = ctx.needs_input_grad
+        if torch.is_grad_enabled():
+            RenderNetTrainFunction.last_backward = "autograd-composite (create_graph)"
+            with torch.enable_grad():
+                x0 = torch.cat([points, _pe_torch(view_dirs, ctx.pe_w, 4), normals, feats], 1)
+                out = _plain_composite(x0, Ws, bs)
+                allin = [points, normals, view_dirs, feats] + list(Ws) + list(bs)
+                ins = [t for t in allin if t.requires_grad]
+                gr = iter(torch.autograd.grad([out], ins, [g_out], create_graph=True, allow_unused=True))
+            res = [next(gr) if t.requires_grad else None for t in allin]
+            return (*res[:4], None, *res[4:])
+        RenderNetTrainFunction.last_backward = "fused-tcgen05"
+        dX0, dW, db = _plain_mlp_backward(g_out.contiguous().float(), Ws, acts, any(need[5:]), any(need[:4]))
+        dp = dn = dv = df = None
+        if need[0]:
+            dp = dX0[:, 0:3].contiguous()
+        if need[1]:
+            dn = dX0[:, 30:33].contiguous()
+        if need[2]:
+            dv = pe_backward(view_dirs.detach().contiguous(), dX0[:, 3:], None, ctx.pe_w, 4)
+        if need[3]:
+            df = dX0[:, 33:289].contiguous()
+        return (dp, dn, dv, df, None, *dW, *db)
+
+
 TRANSLATOR_LAYER_SHAPES = [(512, 167), (512, 512), (512, 512), (512, 512), (3, 512)]
 
 
@@ -793,6 +938,39 @@ def c2f_todo_mask(is_boundary, done):
         check(_lib.load().recmv_c2f_todo_mask(_ptr(is_boundary.view(torch.uint8)), _ptr(done.view(torch.uint8)),
                                               _ptr(todo), D, H, W, _stream(todo)), "recmv_c2f_todo_mask")
     return todo.view(torch.bool)
+
+
+def fragment_decode(pix_to_face, bary, verts, faces, mask=None, camera=None):
+    """Fragments -> (batch, row, col, seed points, face ids[, rays]) of the covered pixels in (n, row, col) order
+    (recmv_fragment_decode).  camera = (fx, fy, px, py, R [3,3]) as host numbers / CPU tensor, or None.
+    One host synchronisation: the read of the row count (the reference's `nonzero` has the same one)."""
+    pix_to_face = pix_to_face.contiguous().long()
+    bary = bary.contiguous().float()
+    _check_input(pix_to_face, "pix_to_face")
+    N, H, W, K = pix_to_face.shape
+    dev = pix_to_face.device
+    verts = verts.detach().contiguous().float()
+    faces = faces.contiguous().long()
+    npix = N * H * W
+    lib = _lib.load()
+    scratch = torch.empty((lib.recmv_fragment_decode_scratch_bytes(npix),), dtype=torch.uint8, device=dev)
+    ob, orow, ocol, ofi = (torch.empty((npix,), dtype=torch.int64, device=dev) for _ in range(4))
+    opts = torch.empty((npix, 3), dtype=torch.float32, device=dev)
+    orays = torch.empty((npix, 3), dtype=torch.float32, device=dev) if camera is not None else None
+    cam = None
+    if camera is not None:
+        fx, fy, px, py, R = camera
+        cam = (c_float * 13)(float(fx), float(fy), float(px), float(py), *[float(v) for v in torch.as_tensor(R).reshape(-1).tolist()])
+    counters = torch.zeros((1,), dtype=torch.int32, device=dev)
+    if mask is not None:
+        mask = mask.contiguous().float()
+    with torch.cuda.device(dev):
+        check(lib.recmv_fragment_decode(_ptr(pix_to_face), _ptr(bary), N, H, W, K, _ptr(verts), _ptr(faces), int(faces.shape[0]),
+                                        _ptr(mask), cam, _ptr(scratch), _ptr(ob), _ptr(orow), _ptr(ocol), _ptr(opts), _ptr(ofi),
+                                        _ptr(orays), _ptr(counters), _stream(bary)), "recmv_fragment_decode")
+    n = int(counters.item())
+    out = (ob[:n], orow[:n], ocol[:n], opts[:n], ofi[:n])
+    return out + (orays[:n],) if camera is not None else out
 
 
 class C2fLevel:

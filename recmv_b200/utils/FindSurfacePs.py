@@ -19,6 +19,9 @@ def FindSurfacePs(TmpVs, TmpFaces, frags):
     .bary_coords [N,H,W,K,3]."""
     pix_to_face = frags.pix_to_face
     bary = frags.bary_coords
+    if pix_to_face.is_cuda and bary.dtype == torch.float32 and not TmpVs.requires_grad:
+        from .. import ops      # one ordered compaction on the device (csrc/fragments.cu)
+        return ops.fragment_decode(pix_to_face, bary, TmpVs, TmpFaces)
     N, H, W, K = pix_to_face.shape
     inner = (bary > 0.0).all(-1) & (pix_to_face >= 0)                # [N,H,W,K]
     # first valid k per pixel (the reference takes a scatter-min over the nonzero columns, :26-30)
@@ -32,6 +35,15 @@ def FindSurfacePs(TmpVs, TmpFaces, frags):
     ws = torch.gather(bary[covered], 1, k.view(-1, 1, 1).expand(-1, 1, 3)).view(-1, 3)
     initTmpPs = (TmpVs[TmpFaces[finds].view(-1)].view(-1, 3, 3) * ws[:, :, None]).sum(1)
     return batch_inds, row_inds, col_inds, initTmpPs, finds
+
+
+def FindSurfacePsRays(TmpVs, TmpFaces, frags, camera, gt_masks=None):
+    """FindSurfacePs + the ground-truth mask selection and the per-pixel view rays of sample_train_ray
+    (OptimGarmentNetwork.py:1006-1011, 1046-1050; CameraMine.view_rays :146-167) in one device pass.
+    camera = (fx, fy, px, py, R) host values of the (shared) RectifiedPerspectiveCameras entry.
+    Returns (batch, row, col, init points, face ids, rays)."""
+    from .. import ops
+    return ops.fragment_decode(frags.pix_to_face, frags.bary_coords, TmpVs, TmpFaces, gt_masks, camera)
 
 
 # The three Optimize* entry points run the whole loop on the device (one C call) when both networks are on the

@@ -129,6 +129,40 @@ def test_findsurfaceps_on_device_matches_reference_golden():
     assert all(x.numel() == 0 for x in e[:3]) and e[3].shape == (0, 3)
 
 
+def test_fragment_decode_with_mask_and_view_rays():
+    """(f3): FindSurfacePs + the gt-mask selection and view_rays of sample_train_ray in one device pass, against the
+    composition of the reference formulas in torch (CameraMine.py:146-167, OptimGarmentNetwork.py:1006-1011)."""
+    from recmv_b200.utils import FindSurfacePs, FindSurfacePsRays
+
+    class Frags:
+        def __init__(self, p2f, bary):
+            self.pix_to_face, self.bary_coords = p2f, bary
+    g = synth.generator(123)
+    V, Fc, N, H, W, K = 300, 500, 3, 64, 48, 2
+    verts = torch.randn((V, 3), generator=g).to(DEV)
+    faces = torch.randint(0, V, (Fc, 3), generator=g).to(DEV)
+    p2f = torch.randint(-1, N * Fc, (N, H, W, K), generator=g)
+    p2f[torch.rand((N, H, W, K), generator=g) < 0.5] = -1
+    bary = torch.rand((N, H, W, K, 3), generator=g)
+    bary[torch.rand((N, H, W, K), generator=g) < 0.2] *= -1.0
+    mask = (torch.rand((N, H, W), generator=g) > 0.3).float().to(DEV)
+    fr = Frags(p2f.to(DEV), bary.to(DEV))
+    fx, fy, px, py = 1.2 * W, 1.1 * W, W / 2 - 0.3, H / 2 + 0.2
+    R = torch.linalg.qr(torch.randn((3, 3), generator=g))[0]
+    b, r, c, pts, fi = FindSurfacePs(verts, faces, fr)                      # device pass, no mask
+    sel = mask[b, r, c] > 0.
+    ps = torch.stack([c[sel].float(), r[sel].float(), torch.ones_like(c[sel]).float()], 1)
+    rays = torch.zeros_like(ps)
+    rays[:, 0] = -ps[:, 0] / fx + ps[:, 2] * px / fx
+    rays[:, 1] = -ps[:, 1] / fy + ps[:, 2] * py / fy
+    rays[:, 2] = ps[:, 2]
+    rays = (rays / torch.norm(rays, p=2, dim=1, keepdim=True)).matmul(R.to(DEV).transpose(0, 1))
+    b2, r2, c2, pts2, fi2, rays2 = FindSurfacePsRays(verts, faces, fr, (fx, fy, px, py, R), mask)
+    assert torch.equal(b2, b[sel]) and torch.equal(r2, r[sel]) and torch.equal(c2, c[sel]) and torch.equal(fi2, fi[sel])
+    assert torch.equal(pts2, pts[sel]) and (rays2 - rays).abs().max() < 1e-6
+    assert (rays2.norm(dim=1) - 1).abs().max() < 1e-5 and b2.numel() > 1000
+
+
 def test_fp16_operand_range_is_reported_not_silent():
     """|a| >= 1023.5 or |w| >= 63.97 leave the fp16 range of the tcgen05 operands.  The kernels saturate
     and raise status code 2; recmv_check_async_errors reports it (and later launches are refused until cleared)."""

@@ -205,7 +205,7 @@ def test_fused_deformer_jacobian_matches_autograd():
     assert deformer.defs[0].last_path == "fused-deformer-jvp"
     pts = t["ps"].clone().requires_grad_(True)
     ds_ref = deformer(pts, defconds, t["batch_inds"], ratio=RATIO, offset_type="body")
-    assert deformer.defs[0].last_path == "autograd-composite"
+    assert deformer.defs[0].last_path == "fused-train"      # translator on the tcgen05 training path, LBS on the CUDA sampler
     J_ref = U.compute_Jacobian(pts, ds_ref, False, False)
     print(f"fused deformer JVP: ds {norm_err(ds, ds_ref):.2e}  J {norm_err(J, J_ref):.2e}")
     assert norm_err(ds, t["ds"]) < 1e-4 and norm_err(J, J_ref) < 2e-4

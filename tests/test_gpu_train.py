@@ -135,3 +135,72 @@ def test_create_graph_goes_through_the_torch_graph_and_matches():
     for a, b in zip(p1, p2):
         assert merr(a, b) < 2e-3
     net.train_fused = True
+
+
+def _grad_rows(prefix, named_params, g):
+    rows = []
+    for name, prm in named_params:
+        key = name.replace(".", "_")
+        gv = prm.grad
+        if f"f64_{key}_sample" in g:
+            for part, ours in (("sample", gv[::16, ::8]), ("rowsum", gv.double().sum(1)), ("colsum", gv.double().sum(0))):
+                scale = float(g[f"f64_{key}_absmax"]) * (1 if part == "sample" else 16)
+                e = float((torch.as_tensor(ours).double().cpu() - torch.from_numpy(g[f"f64_{key}_{part}"]).double()).abs().max()) / scale
+                e_ref = float(np.abs(g[f"f32_{key}_{part}"].astype(np.float64) - g[f"f64_{key}_{part}"]).max()) / scale
+                rows.append((f"{prefix}{key}_{part}", e, e_ref))
+        else:
+            rows.append((prefix + key, merr(gv, g["f64_" + key]), merr(g["f32_" + key], g["f64_" + key])))
+    return rows
+
+
+def test_translator_backward_matches_reference_autograd():
+    """MLPTranslator (model/Deformer.py:171-206) on the tcgen05 training path vs the reference class's autograd."""
+    import recmv_b200.model as M
+    g = load_golden("translator_bwd.npz")
+    gi = load_golden("translator.npz")
+    torch.manual_seed(1)
+    tr = testing.perturb_module(M.MLPTranslator(128, 6), 202, scale=0.5).to(DEV)
+    p = torch.from_numpy(gi["p"]).to(DEV).requires_grad_(True)
+    conds = torch.from_numpy(gi["conds"]).to(DEV).requires_grad_(True)
+    binds = torch.from_numpy(gi["batch_inds"]).to(DEV)
+    out = tr(p, conds, binds, ratio={"deformerRatio": 0.6}, offset_type="body")
+    assert tr.last_path == "fused-train" and merr(out, gi["out"]) < 2e-5
+    (out * torch.from_numpy(g["cot"]).to(DEV)).sum().backward()
+    assert ops.TranslatorTrainFunction.last_backward == "fused-tcgen05"
+    rows = [("dp", merr(p.grad, g["dp_f64"]), merr(g["dp_f32"], g["dp_f64"])),
+            ("dconds", merr(conds.grad, g["dconds_f64"]), merr(g["dconds_f32"], g["dconds_f64"]))]
+    rows += _grad_rows("", sorted(tr.named_parameters()), g)
+    table = "\n".join(f"translator/{n}: |ours-f64| {a:.2e}  |ref32-f64| {b:.2e}" for n, a, b in rows)
+    print(table)
+    for n, a, b in rows:
+        assert a < (1e-4 if n.endswith("sum") else 3e-5), table
+    # [N, V, 3] call form and second order through the torch fallback
+    p2 = torch.from_numpy(gi["p"][:1500]).to(DEV).view(3, 500, 3).requires_grad_(True)
+    o2 = tr(p2, conds, None, ratio={"deformerRatio": 0.6}, offset_type="b2")
+    gr = torch.autograd.grad(o2.sum(), p2, create_graph=True)[0]
+    gr.pow(2).sum().backward()
+    assert "create_graph" in ops.TranslatorTrainFunction.last_backward and torch.isfinite(p2.grad).all()
+
+
+def test_rendernet_backward_matches_reference_autograd():
+    """RenderingNetwork_view_norm (model/RenderNet.py:59-96) on the tcgen05 training path vs the reference's autograd."""
+    import recmv_b200.model as M
+    g = load_golden("rendernet_bwd.npz")
+    torch.manual_seed(2)
+    rn = M.RenderingNetwork_view_norm(256, d_in=9, d_out=3, dims=[512] * 4, mode="idr", weight_norm=True,
+                                      multires_v=4, multires_n=0)
+    rn = testing.perturb_module(rn, 303).to(DEV)
+    ins = [torch.from_numpy(g[k]).to(DEV).requires_grad_(True) for k in ("points", "normals", "view_dirs", "feats")]
+    col = rn(ins[0], ins[1], ins[2], ins[3], {"renderRatio": 0.8})
+    assert rn.last_path == "fused-train"
+    (col * torch.from_numpy(g["cot"]).to(DEV)).sum().backward()
+    assert ops.RenderNetTrainFunction.last_backward == "fused-tcgen05"
+    rows = [("dpoints", merr(ins[0].grad, g["dpoints_f64"]), merr(g["dpoints_f32"], g["dpoints_f64"])),
+            ("dnormals", merr(ins[1].grad, g["dnormals_f64"]), merr(g["dnormals_f32"], g["dnormals_f64"])),
+            ("dview", merr(ins[2].grad, g["dview_f64"]), merr(g["dview_f32"], g["dview_f64"])),
+            ("dfeats", merr(ins[3].grad[:, ::8], g["dfeats_f64"]), merr(g["dfeats_f32"], g["dfeats_f64"]))]
+    rows += _grad_rows("", sorted(rn.named_parameters()), g)
+    table = "\n".join(f"rendernet/{n}: |ours-f64| {a:.2e}  |ref32-f64| {b:.2e}" for n, a, b in rows)
+    print(table)
+    for n, a, b in rows:
+        assert a < (1e-4 if n.endswith("sum") else 3e-5), table
