@@ -278,6 +278,17 @@ def secondary_rates(dev, ren, mode):
                 "includes": "weight-norm graph, cotangent packing, 9 backward-data launches, 1 weight-gradient launch, "
                             "PE Jacobian, autograd bookkeeping (everything loss.backward() runs)"}
     train = rate_train()
+    # the same step through torch autograd over cuBLAS fp32 (what the reference runs): informative, same GPU, same run
+    sdf_net.train_fused = False
+    allow = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = rate_train()
+    finally:
+        sdf_net.train_fused = True
+        torch.backends.cuda.matmul.allow_tf32 = allow
+    train["torch_autograd_cublas_fp32_ms_per_step"] = ref["ms_per_step"]
+    train["speedup_vs_torch_autograd"] = ref["ms_per_step"] / train["ms_per_step"]
 
     return {
         "sdf_train_step (fused forward + tcgen05 backward, loss.backward())": train,

@@ -74,7 +74,7 @@ def test_bwd_weight_matches_fp64(P):
     dW2, _ = ops.mlp_bwd_weight(Gs, Xs, [d[0] for d in dims], [d[1] for d in dims], [1.0, 0.5, 1.0, 1.0], dyn, want_bias=False)
     for (o, i, _), Gl, Xl, w, b, sc, w2 in zip(dims, Gs, Xs, dW, db, [1.0, 0.5, 1.0, 1.0], dW2):
         ref = (Gl[:, :o].double().t() @ Xl[:, :i].double()) * sc
-        assert w.shape == (o, i) and merr(w, ref) < 5e-6, merr(w, ref)
+        assert w.shape == (o, i) and merr(w, ref) < 1e-5, merr(w, ref)
         assert merr(b, Gl[:, :o].double().sum(0)) < 3e-6
         assert torch.equal(w, w2)                                     # deterministic (no atomics on dW)
 
