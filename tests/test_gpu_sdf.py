@@ -130,6 +130,39 @@ def test_sdf_c1_error_against_fp64_truth(name, mode, tag):
         assert r[4] < F64_BOUND[name] + r[3], table
 
 
+def test_accumulation_gain_on_a_network_it_was_not_calibrated_on():
+    """The epilogue multiplies raw accumulators by 1 + 4 * 2^-24 * (K / 64) to undo the tensor core's truncating
+    accumulation (recmv_tc_set_acc_gain); the constant was calibrated on the two golden networks.  Validation on a THIRD,
+    differently scaled network (5x larger perturbation, other seed, other points): against the float64 evaluation of the
+    same weights (oracle, CPU) the tc3 result stays inside the parity bound, its signed error is centred (no residual
+    bias towards zero), and switching the compensation off makes it clearly worse."""
+    net = testing.build_sdf(getTmpSdf, seed=3, perturb_seed=None).to(DEV)
+    testing.perturb_module(net, 777, scale=0.1)
+    net.mlp_mode = _lib.MLP_TC_F16X3
+    x = (torch.rand((8192, 3), generator=synth.generator(99)) * 1.6 - 0.8)
+    Ws, bs = net.effective_weights()
+    truth, tfeat = ot.sdf_mlp(x.double(), [w.detach().cpu().double() for w in Ws], [b.detach().cpu().double() for b in bs],
+                              ot.annealing_weights(6, None))
+    with torch.no_grad():
+        y = net(x.to(DEV), None)[:, 0].cpu().double()
+        feat = net.rendcond.cpu().double()
+    e_on = rel_err(y, truth.view(-1), 1e-2)
+    rowsum_bias = float(((feat - tfeat).sum(1) / tfeat.abs().sum(1)).mean())   # signed, relative: a bias shows here first
+    lib = _lib.load()
+    try:
+        assert lib.recmv_tc_set_acc_gain(_lib.MLP_TC_F16X3, 0.0) == 0
+        with torch.no_grad():
+            y_off = net(x.to(DEV), None)[:, 0].cpu().double()
+            feat_off = net.rendcond.cpu().double()
+    finally:
+        assert lib.recmv_tc_set_acc_gain(_lib.MLP_TC_F16X3, 4.0 * 5.9604645e-8) == 0
+    e_off = rel_err(y_off, truth.view(-1), 1e-2)
+    bias_off = float(((feat_off - tfeat).sum(1) / tfeat.abs().sum(1)).mean())
+    print(f"third network: |tc3 - f64| with gain {e_on:.2e} (signed row-sum bias {rowsum_bias:+.2e}); "
+          f"without {e_off:.2e} (bias {bias_off:+.2e})")
+    assert e_on < 1.5e-4 and abs(rowsum_bias) < 0.3 * abs(bias_off) and e_off > 2 * e_on
+
+
 @pytest.mark.parametrize("name,mode,ntol,tol", MODES)
 def test_render_path_matches_oracle_composition(name, mode, ntol, tol):
     if not _supported(mode):
