@@ -126,14 +126,16 @@ def test_create_graph_goes_through_the_torch_graph_and_matches():
         gr = net.gradient(x)
         loss = ((gr.norm(dim=1) - 1) ** 2).mean()
         loss.backward()
-        return gr.detach(), [p.grad.clone() for p in net.parameters()], x.grad.clone()
+        return gr.detach(), [None if p.grad is None else p.grad.clone() for p in net.parameters()], x.grad.clone()
     g1, p1, x1 = eikonal(True)
     assert net.last_path == "fused-train" and "create_graph" in ops.SdfMlpTrainFunction.last_backward
     g2, p2, x2 = eikonal(False)
     assert net.last_path == "autograd-composite"
     assert merr(g1, g2) < 1e-4 and merr(x1, x2) < 2e-3
     for a, b in zip(p1, p2):
-        assert merr(a, b) < 2e-3
+        assert (a is None) == (b is None)      # e.g. the last bias: the input gradient does not depend on it
+        if a is not None:
+            assert merr(a, b) < 2e-3
     net.train_fused = True
 
 
