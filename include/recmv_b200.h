@@ -299,6 +299,28 @@ RECMV_API int recmv_c2f_scatter(const int32_t* idx, const float* vals, const int
                       recmv_stream_t stream);
 RECMV_API int recmv_c2f_conflict_todo(const uint8_t* conflict_flag, const uint8_t* calculated, const int level[3] /*host*/,
                             const int final_res[3] /*host*/, uint8_t* todo, recmv_stream_t stream);
+/* The fused form Seg3dLossless._forward_device uses -- ONE full-grid pass per level instead of four:
+ *  recmv_c2f_refine       : coarse level (D,H,W) -> fine level (2D-1,2H-1,2W-1): upsampled values (order as
+ *                           recmv_interp2x_boundary3d_fwd), the level's done lattice, and the voxels to query appended to
+ *                           (idx_out, points_out).  The 3x3x3 dilation of the mixed-stencil flags is evaluated exactly
+ *                           from a coarse "mixed cell" mask (mixed_scratch, (D-1)(H-1)(W-1) bytes).
+ *  recmv_c2f_scatter_list : as recmv_c2f_scatter, conflicts appended to conflict_list / conflict_count (zeroed by the
+ *                           caller); clears the claim bytes of the consumed voxels.
+ *  recmv_c2f_mark_conflicts: next worklist = not-yet-evaluated 3x3x3 neighbours of the conflicting voxels, each claimed
+ *                           once through `claim` (level-lattice bytes, 4-byte aligned, all zero between rounds).      */
+RECMV_API int recmv_c2f_refine(const float* occ_coarse, const uint8_t* done_coarse, int D, int H, int W,
+                     const int final_res[3] /*host*/, const float b_min[3] /*host*/, const float b_max[3] /*host*/,
+                     float balance_value, int order, uint8_t* mixed_scratch, float* occ_fine, uint8_t* done_fine,
+                     int32_t* idx_out, float* points_out, int32_t* counters, int capacity, recmv_stream_t stream);
+RECMV_API int recmv_c2f_scatter_list(const int32_t* idx, const float* vals, const int32_t* counters, int capacity,
+                           const int level[3] /*host*/, const int final_res[3] /*host*/, float* occ, uint8_t* done,
+                           uint8_t* calculated, uint8_t* claim, float balance_value, int32_t* conflict_list,
+                           int32_t* conflict_count, int32_t* stats, recmv_stream_t stream);
+RECMV_API int recmv_c2f_mark_conflicts(const int32_t* conflict_list, const int32_t* conflict_count, int list_capacity,
+                             const uint8_t* calculated, const int level[3] /*host*/, const int final_res[3] /*host*/,
+                             const float b_min[3] /*host*/, const float b_max[3] /*host*/, uint8_t* claim,
+                             int32_t* idx_out, float* points_out, int32_t* counters, int capacity,
+                             recmv_stream_t stream);
 
 /* ---- A10: surface-point solve of a batch of rays on the device (utils/FindSurfacePs.py:145-353) -------------------
  * ps [P,3]: in = seeds (FindSurfacePs), out = solution; ok [P] = converged (|f| < dthreshold and the angle between

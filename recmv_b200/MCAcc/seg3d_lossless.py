@@ -124,7 +124,6 @@ class Seg3dLossless(nn.Module):
         b_min, b_max = self.b_min.view(-1).tolist(), self.b_max.view(-1).tolist()
         packed, pe_w = net.packed_weights(), net._pe_weights(ratio)
         calculated = torch.zeros((Df, Hf, Wf), dtype=torch.uint8, device=dev)
-        stats = torch.zeros((2,), dtype=torch.int32, device=dev)
         self.stats = []
         occ, done = None, None
         for li, res in enumerate(self.resolutions):
@@ -138,20 +137,16 @@ class Seg3dLossless(nn.Module):
                 calculated[::stride[2], ::stride[1], ::stride[0]] = 1
                 self.stats.append((W, H, D, D * H * W))
                 continue
-            occ, boundary = ops.interp2x_boundary3d_forward(occ, self.balance_value, 0 if self.use_cuda_impl else 1)
-            done = ops.c2f_done_up(done)
-            todo = ops.c2f_todo_mask(boundary[0, 0], done.view(torch.bool)).view(torch.uint8)
             total = D * H * W
-            lvl = ops.C2fLevel((W, H, D), (Wf, Hf, Df), b_min, b_max, dev, total if total <= (1 << 22) else total // 4)
-            cflag = torch.empty((D, H, W), dtype=torch.uint8, device=dev)
-            stats.zero_()
-            lvl.query(todo, packed, pe_w, mode, occ, done, calculated, cflag, self.balance_value, stats)
+            Dc, Hc, Wc = occ.shape[2:]
+            lvl = ops.C2fLevel((Dc, Hc, Wc), (Wf, Hf, Df), b_min, b_max, dev, total if total <= (1 << 22) else total // 4)
+            occ, done = lvl.refine(occ, done, self.balance_value, 0 if self.use_cuda_impl else 1)
+            lvl.evaluate(packed, pe_w, mode, occ, done, calculated, self.balance_value)
             while True:
-                for _ in range(2):      # conflict rounds, queued speculatively (an empty worklist costs a few no-op launches)
-                    lvl.conflict_todo(cflag, calculated, todo)
-                    lvl.query(todo, packed, pe_w, mode, occ, done, calculated, cflag, self.balance_value, stats)
-                # the level's one host synchronisation: {queried, conflicts of the last round, count, overflow}
-                queried, conflicts, _, overflow = (int(v) for v in torch.cat([stats, lvl.counters]).tolist())
+                for _ in range(2):      # conflict rounds, queued speculatively (an empty list costs three near-empty launches)
+                    lvl.next_from_conflicts(calculated)
+                    lvl.evaluate(packed, pe_w, mode, occ, done, calculated, self.balance_value)
+                queried, conflicts, overflow = lvl.read()                    # the level's one host synchronisation
                 if overflow:
                     return None                                              # worklist overflow: caller falls back
                 if conflicts == 0:

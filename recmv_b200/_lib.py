@@ -104,6 +104,13 @@ SIGNATURES = {
     "recmv_c2f_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "recmv_c2f_conflict_todo": (c_int, [c_void_p, c_void_p, POINTER(c_int), POINTER(c_int), c_void_p, c_void_p]),
+    "recmv_c2f_refine": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_float), POINTER(c_float),
+                                 c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "recmv_c2f_scatter_list": (c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(c_int), POINTER(c_int), c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "recmv_c2f_mark_conflicts": (c_int, [c_void_p, c_void_p, c_int, c_void_p, POINTER(c_int), POINTER(c_int),
+                                         POINTER(c_float), POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                         c_void_p]),
     "recmv_sdf_mlp_fwd_counted": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int64, c_void_p, c_int,
                                           c_void_p]),
     "recmv_surface_solve_workspace": (c_size_t, [c_int64]),

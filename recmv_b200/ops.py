@@ -974,11 +974,15 @@ def fragment_decode(pix_to_face, bary, verts, faces, mask=None, camera=None):
 
 
 class C2fLevel:
-    """Device worklist of one pyramid level (recmv_c2f_*): todo mask -> (index, point) list -> fused SDF launch with a
-    device-side count -> scatter + conflict flags; no host round trip inside a round."""
+    """Device worklist of one pyramid level (recmv_c2f_refine / recmv_sdf_mlp_fwd_counted / recmv_c2f_scatter_list /
+    recmv_c2f_mark_conflicts): one fused full-grid pass builds the level and its worklist, conflict rounds are driven by
+    lists; no host round trip inside the level."""
 
-    def __init__(self, level_whd, final_whd, b_min, b_max, device, capacity):
-        self.level = (ctypes.c_int * 3)(*[int(v) for v in level_whd])
+    def __init__(self, coarse_dhw, final_whd, b_min, b_max, device, capacity):
+        D, H, W = coarse_dhw
+        self.coarse = (int(D), int(H), int(W))
+        self.D, self.H, self.W = 2 * D - 1, 2 * H - 1, 2 * W - 1
+        self.level = (ctypes.c_int * 3)(self.W, self.H, self.D)
         self.final = (ctypes.c_int * 3)(*[int(v) for v in final_whd])
         self.bmin = (c_float * 3)(*[float(v) for v in b_min])
         self.bmax = (c_float * 3)(*[float(v) for v in b_max])
@@ -987,28 +991,53 @@ class C2fLevel:
         self.idx = torch.empty((self.cap,), dtype=torch.int32, device=device)
         self.pts = torch.empty((self.cap, 3), dtype=torch.float32, device=device)
         self.vals = torch.empty((self.cap, 1), dtype=torch.float32, device=device)
-        self.counters = torch.zeros((2,), dtype=torch.int32, device=device)    # count, overflow
+        self.clist = [torch.empty((self.cap,), dtype=torch.int32, device=device) for _ in range(2)]
+        # [0:2] worklist {count, overflow}; [2], [3] conflict counts of the two lists; [4] queried total
+        self.ctr = torch.zeros((8,), dtype=torch.int32, device=device)
+        self.claim = torch.zeros((self.D, self.H, self.W), dtype=torch.uint8, device=device)
+        self.mixed = torch.empty((max(D - 1, 1) * max(H - 1, 1) * max(W - 1, 1),), dtype=torch.uint8, device=device)
+        self.cur = 0     # which conflict list the last scatter filled
 
-    def query(self, todo_u8, packed, pe_w, mode, occ, done_u8, calculated_u8, cflag_u8, balance, stats):
+    def refine(self, occ_coarse, done_coarse, balance, order):
+        occ_f = torch.empty((1, 1, self.D, self.H, self.W), dtype=torch.float32, device=self.dev)
+        done_f = torch.empty((self.D, self.H, self.W), dtype=torch.uint8, device=self.dev)
+        D, H, W = self.coarse
+        with torch.cuda.device(self.dev):
+            check(_lib.load().recmv_c2f_refine(_ptr(occ_coarse), _ptr(done_coarse), D, H, W, self.final, self.bmin, self.bmax,
+                                               float(balance), int(order), _ptr(self.mixed), _ptr(occ_f), _ptr(done_f),
+                                               _ptr(self.idx), _ptr(self.pts), _ptr(self.ctr), self.cap, _stream(occ_f)),
+                  "recmv_c2f_refine")
+        return occ_f, done_f
+
+    def evaluate(self, packed, pe_w, mode, occ, done_u8, calculated_u8, balance):
+        """SDF on the current worklist, scatter, conflicts -> the other conflict list."""
         lib = _lib.load()
+        self.cur ^= 1
+        cc = self.ctr[2 + self.cur:3 + self.cur]
         with torch.cuda.device(self.dev):
             st = _stream(occ)
-            self.counters[0:1].zero_()          # overflow is sticky for the level
-            check(lib.recmv_c2f_compact(_ptr(todo_u8), self.level, self.final, self.bmin, self.bmax, _ptr(self.idx),
-                                        _ptr(self.pts), _ptr(self.counters), self.cap, st), "recmv_c2f_compact")
             check(lib.recmv_sdf_mlp_fwd_counted(_ptr(self.pts), _ptr(packed), _pe_array(pe_w), _ptr(self.vals), None,
-                                                self.cap, _ptr(self.counters), mode, st), "recmv_sdf_mlp_fwd_counted")
-            cflag_u8.zero_()
-            stats[1:2].zero_()                  # conflicts of THIS round
-            check(lib.recmv_c2f_scatter(_ptr(self.idx), _ptr(self.vals), _ptr(self.counters), self.cap, self.level,
-                                        self.final, _ptr(occ), _ptr(done_u8), _ptr(calculated_u8), _ptr(cflag_u8),
-                                        float(balance), _ptr(stats), st), "recmv_c2f_scatter")
+                                                self.cap, _ptr(self.ctr), mode, st), "recmv_sdf_mlp_fwd_counted")
+            cc.zero_()
+            check(lib.recmv_c2f_scatter_list(_ptr(self.idx), _ptr(self.vals), _ptr(self.ctr), self.cap, self.level,
+                                             self.final, _ptr(occ), _ptr(done_u8), _ptr(calculated_u8), _ptr(self.claim),
+                                             float(balance), _ptr(self.clist[self.cur]), _ptr(cc), _ptr(self.ctr[4:5]), st),
+                  "recmv_c2f_scatter_list")
 
-    def conflict_todo(self, cflag_u8, calculated_u8, todo_u8):
+    def next_from_conflicts(self, calculated_u8):
+        """Worklist of the next round from the conflict list the last evaluate() filled."""
+        cc = self.ctr[2 + self.cur:3 + self.cur]
         with torch.cuda.device(self.dev):
-            check(_lib.load().recmv_c2f_conflict_todo(_ptr(cflag_u8), _ptr(calculated_u8), self.level, self.final,
-                                                      _ptr(todo_u8), _stream(todo_u8)), "recmv_c2f_conflict_todo")
-        return todo_u8
+            self.ctr[0:1].zero_()
+            check(_lib.load().recmv_c2f_mark_conflicts(_ptr(self.clist[self.cur]), _ptr(cc), self.cap, _ptr(calculated_u8),
+                                                       self.level, self.final, self.bmin, self.bmax, _ptr(self.claim),
+                                                       _ptr(self.idx), _ptr(self.pts), _ptr(self.ctr), self.cap,
+                                                       _stream(calculated_u8)), "recmv_c2f_mark_conflicts")
+
+    def read(self):
+        """(queried so far, conflicts of the last round, overflow) -- the level's host synchronisation."""
+        h = self.ctr.tolist()
+        return h[4], h[2 + self.cur], h[1]
 
 
 def c2f_done_up(done_u8):
