@@ -330,6 +330,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly ONE line (the JSON): keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO in
+        # some environments) off it unless the caller asks for NCCL logging explicitly through RECMV_NCCL_DEBUG
+        os.environ["NCCL_DEBUG"] = os.environ.get("RECMV_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     strong = args.scaling == "strong"
