@@ -199,6 +199,30 @@ RECMV_API int recmv_pe_backward(const float* x, const float* g, int64_t ldg, con
                       const float* pe_w /*host*/, int bands, float* dx, int accumulate, int64_t P,
                       recmv_stream_t stream);
 
+/* Second-generation layer GEMMs: operands as fp16 hi / lo PLANES in HBM, fed by TMA (csrc/gemm3_tma.cu) -- every tensor a
+ * later GEMM consumes is written in consumable form by its producer, the main loop converts nothing.
+ *  recmv_split_planes      : fp32 [R][C] (row stride ld) -> planes hi = fp16(s v), lo = fp16(s v - hi), s = scale * (*scale_dev
+ *                            if given); transpose != 0 writes [C][R].  ldp = plane row stride in elements (multiple of 8, plane
+ *                            base 16-byte aligned).  Weights: scale 1024 ([out][in] for the forward, transposed for
+ *                            backward-data); the loss cotangent: scale 64 with scale_dev = the call's dyn scale.
+ *  recmv_pe_forward_planes : recmv_pe_forward + the planes (scale 64) of the same rows.
+ *  recmv_mlp_layer_planes  : one layer.  mode 4 / 5 / 6 = forward with none / softplus(100) / ReLU:
+ *                              Y = act(scale * (A . B^T) + bias);
+ *                            mode 0 / 1 / 2 = backward-data with none / softplus' / ReLU':
+ *                              Y = scale * (A . B^T) * act'(saved_input); columns >= split -> Y2 without the derivative.
+ *                            A planes [M][lda_p] hold 64 (x dyn if a_has_dyn) * value, B planes [N][ldb_p] 1024 * weight; K
+ *                            columns of each are used.  Y fp32 [M][ldy] (+ Y2); y_hi / y_lo (optional) receive the planes
+ *                            of Y's columns < split, scaled 64 (x dyn if planes_with_dyn) -- the next GEMM's A operand.      */
+RECMV_API int recmv_split_planes(const float* in, int64_t ld, int64_t R, int C, float scale, const float* scale_dev /*device*/,
+                       int transpose, void* hi, void* lo, int64_t ldp, recmv_stream_t stream);
+RECMV_API int recmv_pe_forward_planes(const float* x, const float* pe_w /*host*/, int bands, float* out, int64_t ld,
+                            void* out_hi, void* out_lo, int64_t ldp, int64_t P, recmv_stream_t stream);
+RECMV_API int recmv_mlp_layer_planes(const void* a_hi, const void* a_lo, int64_t lda_p, const void* b_hi, const void* b_lo,
+                           int64_t ldb_p, int64_t M, int N, int K, int mode, const float* bias, const float* saved_input,
+                           int64_t lds, float scale, const float* dyn_scale /*device*/, int a_has_dyn, int split, float* Y,
+                           int64_t ldy, float* Y2, int64_t ldy2, void* y_hi, void* y_lo, int64_t ldyp, int planes_with_dyn,
+                           recmv_stream_t stream);
+
 /* ---- A3: sdf and its input gradient (ImplicitNetwork.gradient, model/network.py:121-133; the
  * autograd.grad(sdf, p) of utils/FindSurfacePs.py:176 and OptimGarmentNetwork.py:1171,3192) --------------
  * One forward-mode launch of the tcgen05 kernel: every point occupies four tile rows (value and the three

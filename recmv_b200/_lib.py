@@ -78,6 +78,13 @@ SIGNATURES = {
                                      POINTER(c_float), c_void_p, c_int64, c_void_p]),
     "recmv_pe_backward": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, POINTER(c_float), c_int, c_void_p,
                                   c_int, c_int64, c_void_p]),
+    "recmv_split_planes": (c_int, [c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int64,
+                                   c_void_p]),
+    "recmv_pe_forward_planes": (c_int, [c_void_p, POINTER(c_float), c_int, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                        c_int64, c_void_p]),
+    "recmv_mlp_layer_planes": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_int64, c_float, c_void_p, c_int, c_int, c_void_p, c_int64,
+                                       c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "recmv_translator_packed_bytes": (c_size_t, []),
     "recmv_translator_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "recmv_deformer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, POINTER(c_float),

@@ -1,0 +1,408 @@
+// Training-path layer GEMMs, second generation: forward layers and backward-data with BOTH operands already split into
+// fp16 hi / lo planes in HBM and fed by TMA -- no conversion in the main loop.
+//
+// gemm3.cu converts fp32 operands inside its main loop (eight producer warps: load -> scale -> split -> st.shared); at
+// ~6 us per 64-wide K block against 0.4 us of MMAs that chain bounds it (profiles/r02_notes.md).  Here every tensor a
+// later GEMM consumes is WRITTEN in consumable form by the kernel that produces it:
+//   * a layer's output  Y  -> fp32 [P][ld] (activation derivative, weight gradient) AND two fp16 planes [P][ldp]
+//     hi = fp16(64 y), lo = fp16(64 y - hi)  (K-major rows: exactly what the next layer's A operand is);
+//   * a cotangent       G  -> fp32 AND planes of 64 * dyn * g  (dyn = the call's power-of-two gradient scale, device scalar);
+//   * weights           W  -> planes of 1024 w, once per step: [out][in] for the forward, [in][out] for backward-data
+//     (recmv_split_planes, optionally transposing).
+// Main loop = the inference engine's recipe on one CTA: a TMA thread streams [128 rows x 64 k] SW128 boxes of the four
+// planes through a 3-stage ring (complete_tx on the stage's mbarrier; out-of-range rows / columns are zero-filled by TMA,
+// so ragged M, N, K need no masking), one thread issues 12 tcgen05 MMAs per K block (lo*hi, hi*lo, hi*hi), tcgen05.commit
+// frees the stage.  PERSISTENT: a CTA walks tiles blockIdx.x, + gridDim.x, ...; the two 128-column TMEM accumulators
+// alternate per tile, so the four epilogue warps (bias / activation or activation derivative, fp32 store, hi / lo split and
+// plane store) work on tile i while tile i + 1's loads and MMAs run.
+#include "sdf_mlp.cuh"
+#include "tc_common.cuh"
+
+namespace recmv {
+using namespace tc;
+
+namespace {
+
+constexpr int kBM = 128, kBN = 128, kBK = 64;
+constexpr int kStages = 3;
+constexpr uint32_t kPlane = 16384;                 // one [128 rows][64 fp16] tile
+constexpr uint32_t kStageBytes = 4 * kPlane;       // A hi | A lo | B hi | B lo
+constexpr int kEpiWarps = 16;                      // 4 per TMEM lane quadrant, one 32-column group of the 128-column tile each:
+                                                   // with 4 warps the epilogue (activation, fp32 store, hi / lo split, plane
+                                                   // store for 128 values per thread) took ~30 us per tile against ~8 us of
+                                                   // main loop and bounded the kernel (r02_launches_train_131k_planes.csv)
+constexpr int kThreads = 32 * (2 + kEpiWarps);     // warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator
+constexpr uint32_t kOffBar = kStages * kStageBytes;
+constexpr int kBarFull = 0, kBarEmpty = kStages, kBarAccFull = 2 * kStages, kBarAccEmpty = 2 * kStages + 2;
+constexpr int kNumBars = 2 * kStages + 4;
+constexpr uint32_t kOffMisc = kOffBar + kNumBars * 8;
+constexpr uint32_t kSmemBytes = kOffMisc + 64 + 1024 /* alignment slack */;
+
+enum { TEPI_BWD_NONE = 0, TEPI_BWD_SOFTPLUS100 = 1, TEPI_BWD_RELU = 2, TEPI_FWD_NONE = 4, TEPI_FWD_SOFTPLUS100 = 5,
+       TEPI_FWD_RELU = 6 };
+
+struct GtParams {
+  float* D; long long ldd;                 // fp32 output, columns n < split
+  float* D2; long long ldd2;               // fp32 output, columns n >= split (no activation derivative), may be NULL
+  __half* DH; __half* DL; long long ldp;   // optional planes of the < split columns: split(plane_scale * value)
+  const float* E; long long lde;           // saved layer input (backward-data activation derivative)
+  const float* bias;                       // forward
+  const float* dyn_scale;                  // backward-data: device scalar in the A planes' scale
+  float unscale;                           // d_scale / (a_scale * b_scale), before dyn
+  float plane_scale;                       // 64 (x dyn for cotangents)
+  int M, N, K, split, tiles_m, tiles_n, epi, dyn_in_planes;
+  DevStatus* status;
+};
+
+__device__ __forceinline__ void umma_f16_1cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_1cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// 2-D tile load into this CTA's shared memory; completion bytes on a local mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm3_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const GtParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kOffBar;
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(gbase + kOffMisc + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kOffMisc);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = prm.tiles_m * prm.tiles_n;
+  const int nkb = (prm.K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int s = 0; s < kStages; ++s) { mbar_init(BAR(kBarFull + s), 1); mbar_init(BAR(kBarEmpty + s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 1); mbar_init(BAR(kBarAccEmpty + b), kEpiWarps); }
+    fence_mbar_init();
+    prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================================== TMA producer =======================================================
+    if (lane == 0) {
+      long long kbg = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tm = tile / prm.tiles_n, tn = tile - tm * prm.tiles_n;
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = (int)(kbg % kStages);
+          const uint32_t par = (uint32_t)((kbg / kStages) & 1);
+          mbar_wait(BAR(kBarEmpty + s), par ^ 1u, abort_flag, prm.status, 3000 + s);
+          const uint32_t st = base + (uint32_t)s * kStageBytes;
+          mbar_expect_tx_local(BAR(kBarFull + s), kStageBytes);
+          tma_load_2d(st, &tm_a_hi, BAR(kBarFull + s), kb * kBK, tm * kBM);
+          tma_load_2d(st + kPlane, &tm_a_lo, BAR(kBarFull + s), kb * kBK, tm * kBM);
+          tma_load_2d(st + 2 * kPlane, &tm_b_hi, BAR(kBarFull + s), kb * kBK, tn * kBN);
+          tma_load_2d(st + 3 * kPlane, &tm_b_lo, BAR(kBarFull + s), kb * kBK, tn * kBN);
+        }
+      }
+      // collect the last stage releases (asynchronous tcgen05.commit arrivals) before the CTA may exit
+      for (long long k2 = kbg; k2 < kbg + kStages; ++k2) {
+        if (k2 - kStages < 0) continue;
+        const int s = (int)(k2 % kStages);
+        mbar_wait(BAR(kBarEmpty + s), (uint32_t)(((k2 / kStages) & 1) ^ 1), abort_flag, prm.status, 3050 + s);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================== MMA issuer ========================================================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16(kBM, kBN);
+      long long kbg = 0, item = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++item) {
+        const int buf = (int)(item & 1);
+        mbar_wait(BAR(kBarAccEmpty + buf), (uint32_t)(((item >> 1) & 1) ^ 1), abort_flag, prm.status, 3200 + buf);
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + (uint32_t)(buf * kBN);
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = (int)(kbg % kStages);
+          mbar_wait(BAR(kBarFull + s), (uint32_t)((kbg / kStages) & 1), abort_flag, prm.status, 3100 + s);
+          tc_fence_after();
+          const uint32_t st = base + (uint32_t)s * kStageBytes;
+          const uint64_t a_hi = smem_desc_sw128(st), a_lo = smem_desc_sw128(st + kPlane);
+          const uint64_t b_hi = smem_desc_sw128(st + 2 * kPlane), b_lo = smem_desc_sw128(st + 3 * kPlane);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_1cta(dcol, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb == 0 && k == 0) ? 0u : 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_1cta(dcol, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_1cta(dcol, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+          umma_commit_1cta(BAR(kBarEmpty + s));
+        }
+        umma_commit_1cta(BAR(kBarAccFull + buf));
+      }
+    }
+  } else {
+    // =========================================== epilogue ===========================================================
+    const int q = warp & 3;                    // TMEM lane quadrant of this warp
+    const int cg = (warp - 2) >> 2;            // its 32-column group of the tile
+    const int row = q * 32 + lane;
+    const float dyn = prm.dyn_scale ? __ldg(prm.dyn_scale) : 1.f;
+    // truncating-accumulation compensation: 4 hi*hi MMAs per K block, ~2^-24 each (gemm3.cu)
+    const float unscale = prm.unscale / dyn * (1.f + 4.f * 5.9604645e-8f * (float)nkb);
+    const float pscale = prm.plane_scale * (prm.dyn_in_planes ? dyn : 1.f);
+    const bool fwd = prm.epi >= TEPI_FWD_NONE;
+    long long item = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++item) {
+      const int tm = tile / prm.tiles_n, tn = tile - tm * prm.tiles_n;
+      const int m = tm * kBM + row, n0 = tn * kBN;
+      const int buf = (int)(item & 1);
+      mbar_wait(BAR(kBarAccFull + buf), (uint32_t)((item >> 1) & 1), abort_flag, prm.status, 3400 + buf);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kBN + cg * 32), r);
+        tmem_ld_wait();
+        const int nb = n0 + cg * 32;
+#pragma unroll 1
+        for (int j8 = 0; j8 < 4 && m < prm.M; ++j8) {
+          const int n = nb + 8 * j8;
+          if (n >= prm.N) break;
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[8 * j8 + e]) * unscale;
+          const bool full = n + 8 <= prm.split;                       // the 8 columns are all "activation" columns
+          if (fwd) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (n + e >= prm.N) { o[e] = 0.f; continue; }
+              float v = o[e] + (prm.bias ? __ldg(prm.bias + n + e) : 0.f);
+              if (prm.epi == TEPI_FWD_SOFTPLUS100) v = softplus100(v);
+              else if (prm.epi == TEPI_FWD_RELU) v = fmaxf(v, 0.f);
+              o[e] = v;
+            }
+          } else if (prm.epi != TEPI_BWD_NONE) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if (n + e >= prm.split) continue;
+              const float a = __ldg(prm.E + (long long)m * prm.lde + n + e);
+              o[e] = prm.epi == TEPI_BWD_SOFTPLUS100 ? o[e] * (1.f - __expf(-100.f * a)) : (a > 0.f ? o[e] : 0.f);
+            }
+          }
+          if (full && (prm.ldd & 3) == 0) {
+            float* d = prm.D + (long long)m * prm.ldd + n;
+            *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(d + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int nn = n + e;
+              if (nn >= prm.N) continue;
+              if (nn < prm.split) prm.D[(long long)m * prm.ldd + nn] = o[e];
+              else if (prm.D2) prm.D2[(long long)m * prm.ldd2 + (nn - prm.split)] = o[e];
+            }
+          }
+          if (prm.DH) {   // the same values as the next GEMM's A operand: fp16 hi / lo of plane_scale * value
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (n + e < prm.split) ? o[e] * pscale : 0.f;
+            range_check8(v, prm.status, 3500);
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            if (full && (prm.ldp & 7) == 0) {
+              *reinterpret_cast<uint4*>(prm.DH + (long long)m * prm.ldp + n) = hi;
+              *reinterpret_cast<uint4*>(prm.DL + (long long)m * prm.ldp + n) = lo;
+            } else {
+              const __half* hh = reinterpret_cast<const __half*>(&hi);
+              const __half* ll = reinterpret_cast<const __half*>(&lo);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (n + e < prm.split) { prm.DH[(long long)m * prm.ldp + n + e] = hh[e]; prm.DL[(long long)m * prm.ldp + n + e] = ll[e]; }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(BAR(kBarAccEmpty + buf));
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+namespace {
+
+// fp32 [R][C] (row stride ld) -> fp16 hi / lo planes of scale * value: out[r][c] (transpose == 0, row stride ldp) or
+// out[c][r] (transpose != 0).  scale_dev: optional device scalar multiplied into scale.
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ in, long long ld, long long R, int C,
+                                                           float scale, const float* __restrict__ scale_dev, int transpose,
+                                                           __half* __restrict__ hi, __half* __restrict__ lo, long long ldp,
+                                                           DevStatus* status) {
+  const float s = scale * (scale_dev ? __ldg(scale_dev) : 1.f);
+  const long long total = R * (long long)C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    float v = __ldg(in + r * ld + c) * s;
+    if (!(fabsf(v) < 65504.f)) { report_range(status, 3600); v = fminf(fmaxf(v, -65504.f), 65504.f); }
+    const __half h = __float2half_rn(v);
+    const long long o = transpose ? (long long)c * ldp + r : r * ldp + c;
+    hi[o] = h;
+    lo[o] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// positional encoding as a saved layer input AND as operand planes
+__global__ void __launch_bounds__(256) pe_forward_planes_kernel(const float* __restrict__ x, PeWeights pw, int bands,
+                                                                float* __restrict__ out, long long ld, __half* __restrict__ oh,
+                                                                __half* __restrict__ ol, long long ldp, long long P) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float pe[39];
+  positional_encode(x[3 * p], x[3 * p + 1], x[3 * p + 2], pw.w, pe);
+  const int n = 3 + 6 * bands;
+  for (int e = 0; e < n; ++e) {
+    if (out) out[p * ld + e] = pe[e];
+    const float v = pe[e] * kActScale;
+    const __half h = __float2half_rn(v);
+    oh[p * ldp + e] = h;
+    ol[p * ldp + e] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+int make_plane_tmap(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_elems) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !p) return e != cudaSuccess ? (int)e : (int)cudaErrorNotSupported;
+    fn = (EncodeTiledFn)p;
+  }
+  if (((uintptr_t)base & 15) != 0 || (row_pitch_elems & 7) != 0) return RECMV_E_SHAPE;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_pitch_elems * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+}  // namespace
+}  // namespace recmv
+
+using namespace recmv;
+
+// fp32 [R][C] -> fp16 hi / lo planes of scale (* *scale_dev) * value, optionally transposed ([C][R]); ldp = row stride of the
+// planes in elements (multiple of 8).  Weights: scale 1024; activations 64; cotangents 64 with scale_dev = the dyn scale.
+extern "C" int recmv_split_planes(const float* in, int64_t ld, int64_t R, int C, float scale, const float* scale_dev,
+                                  int transpose, void* hi, void* lo, int64_t ldp, recmv_stream_t stream) {
+  if (R < 0 || C <= 0) return RECMV_E_SHAPE;
+  if (R == 0) return RECMV_OK;
+  if (!in || !hi || !lo) return RECMV_E_NULL;
+  void* sd = nullptr;
+  int s0 = device_status_record(&sd);
+  if (s0) return s0;
+  split_planes_kernel<<<stride_grid(R * (int64_t)C, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      in, ld, R, C, scale, scale_dev, transpose, (__half*)hi, (__half*)lo, ldp, (DevStatus*)sd);
+  return launch_status();
+}
+
+extern "C" int recmv_pe_forward_planes(const float* x, const float* pe_w, int bands, float* out, int64_t ld, void* out_hi,
+                                       void* out_lo, int64_t ldp, int64_t P, recmv_stream_t stream) {
+  if (P < 0 || bands < 0 || bands > 6) return RECMV_E_SHAPE;
+  if (P == 0) return RECMV_OK;
+  if (!x || !pe_w || !out_hi || !out_lo) return RECMV_E_NULL;
+  PeWeights pw;
+  for (int i = 0; i < 12; ++i) pw.w[i] = i < 2 * bands ? pe_w[i] : 0.f;
+  pe_forward_planes_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, pw, bands, out, ld, (__half*)out_hi,
+                                                                                          (__half*)out_lo, ldp, P);
+  return launch_status();
+}
+
+// One layer GEMM with TMA-fed operand planes.
+//   forward       (mode 4/5/6 = none / softplus100 / ReLU):  Y = act(pre_scale * (A . B^T) + bias)
+//   backward-data (mode 0/1/2 = none / softplus100' / ReLU'): Y = (A . B^T) * out_scale * act'(saved_input), columns >= split
+//                 to Y2 without the derivative
+// A planes [M][lda_p] (K columns used, scaled 64 [x dyn when a_has_dyn]), B planes [N][ldb_p] (scaled 1024).
+// Outputs: Y fp32 [M][ldy]; optional planes of the < split columns, scaled 64 (x dyn when planes_with_dyn).
+extern "C" int recmv_mlp_layer_planes(const void* a_hi, const void* a_lo, int64_t lda_p, const void* b_hi, const void* b_lo,
+                                      int64_t ldb_p, int64_t M, int N, int K, int mode, const float* bias,
+                                      const float* saved_input, int64_t lds, float scale, const float* dyn_scale,
+                                      int a_has_dyn, int split, float* Y, int64_t ldy, float* Y2, int64_t ldy2, void* y_hi,
+                                      void* y_lo, int64_t ldyp, int planes_with_dyn, recmv_stream_t stream) {
+  if (M < 0 || N <= 0 || K <= 0) return RECMV_E_SHAPE;
+  if (M == 0) return RECMV_OK;
+  if (!a_hi || !a_lo || !b_hi || !b_lo || !Y) return RECMV_E_NULL;
+  if (!(mode == 0 || mode == 1 || mode == 2 || mode == 4 || mode == 5 || mode == 6)) return RECMV_E_DTYPE;
+  if ((mode == 1 || mode == 2) && !saved_input) return RECMV_E_NULL;
+  if ((y_hi == nullptr) != (y_lo == nullptr)) return RECMV_E_NULL;
+  if (M > (int64_t)1 << 30) return RECMV_E_RANGE;
+  CUtensorMap ta_h, ta_l, tb_h, tb_l;
+  int s = make_plane_tmap(&ta_h, a_hi, (uint64_t)K, (uint64_t)M, (uint64_t)lda_p);
+  if (!s) s = make_plane_tmap(&ta_l, a_lo, (uint64_t)K, (uint64_t)M, (uint64_t)lda_p);
+  if (!s) s = make_plane_tmap(&tb_h, b_hi, (uint64_t)K, (uint64_t)N, (uint64_t)ldb_p);
+  if (!s) s = make_plane_tmap(&tb_l, b_lo, (uint64_t)K, (uint64_t)N, (uint64_t)ldb_p);
+  if (s) return s;
+  static bool done[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!done[dev & 15]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm3_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    done[dev & 15] = true;
+  }
+  void* sd = nullptr;
+  int s0 = device_status_record(&sd);
+  if (s0) return s0;
+  if (((DevStatus*)sd)->code != 0) return RECMV_E_DEVICE;
+  GtParams prm = {};
+  prm.D = Y; prm.ldd = ldy; prm.D2 = Y2; prm.ldd2 = ldy2;
+  prm.DH = (__half*)y_hi; prm.DL = (__half*)y_lo; prm.ldp = ldyp;
+  prm.E = saved_input; prm.lde = lds; prm.bias = bias;
+  prm.dyn_scale = a_has_dyn ? dyn_scale : nullptr;
+  prm.unscale = scale / (kActScale * kWgtScale);
+  prm.plane_scale = kActScale;
+  prm.dyn_in_planes = 0;
+  if (planes_with_dyn) {
+    // cotangent planes carry the dyn scale; when the A planes do not (never the case in backward-data) it would have to be
+    // multiplied in separately
+    if (!a_has_dyn || !dyn_scale) return RECMV_E_UNSUPPORTED;
+    prm.dyn_in_planes = 1;
+  }
+  prm.M = (int)M; prm.N = N; prm.K = K;
+  prm.split = (split > 0 && split < N) ? split : N;
+  prm.tiles_m = (int)((M + kBM - 1) / kBM); prm.tiles_n = (N + kBN - 1) / kBN;
+  prm.epi = mode; prm.status = (DevStatus*)sd;
+  const int total = prm.tiles_m * prm.tiles_n;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm3_tma_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(ta_h, ta_l, tb_h, tb_l, prm);
+  return launch_status();
+}

@@ -430,6 +430,11 @@ def sdf_value_and_grad(x, packed, pe_w=None, mode=None, want_feat=False):
 # Training path: fused forward that saves the layer inputs + tcgen05 backward GEMMs (csrc/gemm3.cu)
 # --------------------------------------------------------------------------------------------------
 ACT_NONE, ACT_SOFTPLUS100, ACT_RELU = 0, 1, 2
+# "planes": forward / backward-data layer GEMMs fed by TMA from fp16 hi / lo operand planes (csrc/gemm3_tma.cu);
+# "producers": the first-generation kernel that converts fp32 operands in its main loop (csrc/gemm3.cu).  The weight
+# gradient uses the latter in both settings.
+import os as _os
+TRAIN_GEMM = _os.environ.get("RECMV_TRAIN_GEMM", "planes")
 _INV_SQRT2 = 0.70710678118654752440
 
 
@@ -493,6 +498,47 @@ def pe_forward(x, pe_w, bands, out, out2=None):
                                            out2.stride(0) if out2 is not None else 0, x.shape[0], _stream(x)),
               "recmv_pe_forward")
     return out
+
+
+def _pad8(n):
+    return (int(n) + 7) // 8 * 8
+
+
+def split_planes(t, rows, cols, scale, scale_dev=None, transpose=False, ldp=None):
+    """fp32 [rows, >= cols] -> (hi, lo) fp16 planes of scale (* scale_dev) * t, [rows][ldp] or transposed [cols][ldp]."""
+    dev = t.device
+    ldp = ldp or _pad8(rows if transpose else cols)
+    shape = (cols, ldp) if transpose else (rows, ldp)
+    hi = torch.zeros(shape, dtype=torch.float16, device=dev)
+    lo = torch.zeros(shape, dtype=torch.float16, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().recmv_split_planes(_ptr(t), t.stride(0), int(rows), int(cols), float(scale), _ptr(scale_dev),
+                                             1 if transpose else 0, _ptr(hi), _ptr(lo), ldp, _stream(t)), "recmv_split_planes")
+    return hi, lo
+
+
+def pe_forward_planes(x, pe_w, bands, out, out_hi, out_lo):
+    w = (c_float * (2 * bands))(*[float(v) for v in pe_w[:2 * bands]])
+    with torch.cuda.device(x.device):
+        check(_lib.load().recmv_pe_forward_planes(_ptr(x), w, int(bands), _ptr(out), out.stride(0) if out is not None else 0,
+                                                  _ptr(out_hi), _ptr(out_lo), out_hi.stride(0), x.shape[0], _stream(x)),
+              "recmv_pe_forward_planes")
+
+
+def mlp_layer_planes(a_planes, b_planes, M, N, K, mode, Y, bias=None, saved_input=None, scale=1.0, dyn=None, a_has_dyn=False,
+                     split=0, Y2=None, y_planes=None, planes_with_dyn=False):
+    """One TMA-fed layer GEMM on operand planes (recmv_mlp_layer_planes); modes: 4/5/6 forward none/softplus/relu,
+    0/1/2 backward-data none/softplus'/relu'."""
+    ah, al = a_planes
+    bh, bl = b_planes
+    yh, yl = y_planes if y_planes is not None else (None, None)
+    with torch.cuda.device(Y.device):
+        check(_lib.load().recmv_mlp_layer_planes(
+            _ptr(ah), _ptr(al), ah.stride(0), _ptr(bh), _ptr(bl), bh.stride(0), int(M), int(N), int(K), int(mode), _ptr(bias),
+            _ptr(saved_input), saved_input.stride(0) if saved_input is not None else 0, float(scale), _ptr(dyn),
+            1 if a_has_dyn else 0, int(split), _ptr(Y), Y.stride(0), _ptr(Y2), Y2.stride(0) if Y2 is not None else 0, _ptr(yh),
+            _ptr(yl), yh.stride(0) if yh is not None else 0, 1 if planes_with_dyn else 0, _stream(Y)), "recmv_mlp_layer_planes")
+    return Y
 
 
 def pe_backward(x, g, g2, pe_w, bands, dx=None):
@@ -559,11 +605,28 @@ class SdfMlpTrainFunction(torch.autograd.Function):
               [torch.empty((P, 512), dtype=torch.float32, device=dev) for _ in range(8)]
         sdf = torch.empty((P, 1), dtype=torch.float32, device=dev)
         feat = torch.empty((P, 256), dtype=torch.float32, device=dev)
-        pe_forward(x, pe_w, 6, act[0], act[4][:, 473:])
-        for l in range(8):
-            mlp_fwd_layer(act[l], Ws[l], bs[l], Ws[l].shape[0], Ws[l].shape[1], ACT_SOFTPLUS100, act[l + 1],
-                          pre_scale=_INV_SQRT2 if l == 4 else 1.0)
-        mlp_fwd_layer(act[8], Ws[8], bs[8], 257, 512, ACT_NONE, sdf, split=1, Y2=feat)
+        if TRAIN_GEMM == "planes":
+            # operands as fp16 hi / lo planes, TMA-fed GEMMs (csrc/gemm3_tma.cu): each layer writes its output in fp32
+            # (kept for the backward) AND as the next layer's A planes
+            xp = [(torch.empty((P, 64), dtype=torch.float16, device=dev), torch.empty((P, 64), dtype=torch.float16, device=dev))]
+            xp += [(torch.empty((P, 512), dtype=torch.float16, device=dev), torch.empty((P, 512), dtype=torch.float16, device=dev))
+                   for _ in range(8)]
+            pe_forward_planes(x, pe_w, 6, act[0], xp[0][0], xp[0][1])
+            pe_forward_planes(x, pe_w, 6, act[4][:, 473:], xp[4][0][:, 473:], xp[4][1][:, 473:])
+            for l in range(9):
+                o, i = Ws[l].shape
+                wp = split_planes(Ws[l], o, i, 1024.0)
+                if l < 8:
+                    mlp_layer_planes(xp[l], wp, P, o, i, 5, act[l + 1], bias=bs[l], scale=_INV_SQRT2 if l == 4 else 1.0,
+                                     y_planes=xp[l + 1])
+                else:
+                    mlp_layer_planes(xp[8], wp, P, 257, 512, 4, sdf, bias=bs[8], split=1, Y2=feat)
+        else:
+            pe_forward(x, pe_w, 6, act[0], act[4][:, 473:])
+            for l in range(8):
+                mlp_fwd_layer(act[l], Ws[l], bs[l], Ws[l].shape[0], Ws[l].shape[1], ACT_SOFTPLUS100, act[l + 1],
+                              pre_scale=_INV_SQRT2 if l == 4 else 1.0)
+            mlp_fwd_layer(act[8], Ws[8], bs[8], 257, 512, ACT_NONE, sdf, split=1, Y2=feat)
         ctx.pe_w, ctx.mode = [float(w) for w in pe_w], mode
         ctx.save_for_backward(x, *Wb, *act)
         return sdf, feat
@@ -591,7 +654,7 @@ class SdfMlpTrainFunction(torch.autograd.Function):
             res = [next(it) if t.requires_grad else None for t in [xi] + list(Ws) + list(bs)]
             return (res[0] if need_x else None, None, None, None, *res[1:])
         SdfMlpTrainFunction.last_backward = "fused-tcgen05"
-        G8 = torch.zeros((P, 260), dtype=torch.float32, device=dev)
+        G8 = torch.zeros((P, 264), dtype=torch.float32, device=dev)
         if g_sdf is not None:
             G8[:, 0:1] = g_sdf
         if g_feat is not None:
@@ -602,16 +665,32 @@ class SdfMlpTrainFunction(torch.autograd.Function):
         dpe4 = torch.empty((P, 40), dtype=torch.float32, device=dev)
         outs = [w.shape[0] for w in Ws]
         ins = [w.shape[1] for w in Ws]
-        for l in range(8, 0, -1):
-            G[l - 1] = torch.empty((P, 512), dtype=torch.float32, device=dev)
-            mlp_bwd_data_layer(G[l], Ws[l], outs[l], ins[l], act[l], ACT_SOFTPLUS100, G[l - 1],
-                               split=473 if l == 4 else 0, D2=dpe4 if l == 4 else None,
-                               out_scale=_INV_SQRT2 if l == 4 else 1.0, dyn_scale=dyn)
         dx = None
-        if need_x:
-            dpe0 = torch.empty((P, 40), dtype=torch.float32, device=dev)
-            mlp_bwd_data_layer(G[0], Ws[0], outs[0], ins[0], None, ACT_NONE, dpe0, dyn_scale=dyn)
-            dx = pe_backward(x, dpe0, dpe4, ctx.pe_w, 6)
+        if TRAIN_GEMM == "planes":
+            gp = split_planes(G8, P, 257, 64.0, scale_dev=dyn, ldp=264)       # cotangent planes carry 64 * dyn
+            for l in range(8, 0, -1):
+                G[l - 1] = torch.empty((P, 512), dtype=torch.float32, device=dev)
+                gprev = (torch.empty((P, 512), dtype=torch.float16, device=dev), torch.empty((P, 512), dtype=torch.float16, device=dev))
+                wtp = split_planes(Ws[l].detach(), outs[l], ins[l], 1024.0, transpose=True)     # [in][out]: B of backward-data
+                mlp_layer_planes(gp, wtp, P, ins[l], outs[l], 1, G[l - 1], saved_input=act[l], scale=_INV_SQRT2 if l == 4 else 1.0,
+                                 dyn=dyn, a_has_dyn=True, split=473 if l == 4 else 0, Y2=dpe4 if l == 4 else None,
+                                 y_planes=gprev, planes_with_dyn=True)
+                gp = gprev
+            if need_x:
+                dpe0 = torch.empty((P, 40), dtype=torch.float32, device=dev)
+                wtp = split_planes(Ws[0].detach(), outs[0], ins[0], 1024.0, transpose=True)
+                mlp_layer_planes(gp, wtp, P, ins[0], outs[0], 0, dpe0, dyn=dyn, a_has_dyn=True)
+                dx = pe_backward(x, dpe0, dpe4, ctx.pe_w, 6)
+        else:
+            for l in range(8, 0, -1):
+                G[l - 1] = torch.empty((P, 512), dtype=torch.float32, device=dev)
+                mlp_bwd_data_layer(G[l], Ws[l], outs[l], ins[l], act[l], ACT_SOFTPLUS100, G[l - 1],
+                                   split=473 if l == 4 else 0, D2=dpe4 if l == 4 else None,
+                                   out_scale=_INV_SQRT2 if l == 4 else 1.0, dyn_scale=dyn)
+            if need_x:
+                dpe0 = torch.empty((P, 40), dtype=torch.float32, device=dev)
+                mlp_bwd_data_layer(G[0], Ws[0], outs[0], ins[0], None, ACT_NONE, dpe0, dyn_scale=dyn)
+                dx = pe_backward(x, dpe0, dpe4, ctx.pe_w, 6)
         dW, db = [None] * 9, [None] * 9
         if need_w:
             dW, db = mlp_bwd_weight(G, list(act), outs, ins, [_INV_SQRT2 if l == 4 else 1.0 for l in range(9)], dyn)
