@@ -704,11 +704,19 @@ def _plain_mlp_forward(X0, Ws, bs):
     bs = [b.detach().contiguous().float() for b in bs]
     acts = [X0]
     n = len(Ws)
+    planes = TRAIN_GEMM == "planes"
+    xp = split_planes(X0, P, Ws[0].shape[1], 64.0, ldp=_pad8(X0.shape[1])) if planes else None
     for l in range(n):
         o, i = Ws[l].shape
         last = l == n - 1
         Y = torch.empty((P, o if not last else ((o + 3) // 4) * 4), dtype=torch.float32, device=dev)
-        mlp_fwd_layer(acts[l], Ws[l], bs[l], o, i, ACT_NONE if last else ACT_RELU, Y)
+        if planes:
+            yp = None if last else (torch.empty((P, _pad8(o)), dtype=torch.float16, device=dev),
+                                    torch.empty((P, _pad8(o)), dtype=torch.float16, device=dev))
+            mlp_layer_planes(xp, split_planes(Ws[l], o, i, 1024.0), P, o, i, 4 if last else 6, Y, bias=bs[l], y_planes=yp)
+            xp = yp
+        else:
+            mlp_fwd_layer(acts[l], Ws[l], bs[l], o, i, ACT_NONE if last else ACT_RELU, Y)
         acts.append(Y)
     return acts[-1][:, :Ws[-1].shape[0]], acts[:-1]
 
@@ -719,18 +727,30 @@ def _plain_mlp_backward(g_out, Ws, acts, need_w, need_x0):
     n = len(Ws)
     o_last = Ws[-1].shape[0]
     G = [None] * n
-    G[n - 1] = torch.zeros((P, ((o_last + 3) // 4) * 4), dtype=torch.float32, device=dev)
+    G[n - 1] = torch.zeros((P, _pad8(o_last)), dtype=torch.float32, device=dev)
     G[n - 1][:, :o_last] = g_out
     dyn = grad_dyn_scale(G[n - 1])
+    planes = TRAIN_GEMM == "planes"
+    gp = split_planes(G[n - 1], P, o_last, 64.0, scale_dev=dyn, ldp=_pad8(o_last)) if planes else None
     for l in range(n - 1, 0, -1):
         o, i = Ws[l].shape
         G[l - 1] = torch.empty((P, i), dtype=torch.float32, device=dev)
-        mlp_bwd_data_layer(G[l], Ws[l], o, i, acts[l], ACT_RELU, G[l - 1], dyn_scale=dyn)
+        if planes:
+            gprev = (torch.empty((P, _pad8(i)), dtype=torch.float16, device=dev), torch.empty((P, _pad8(i)), dtype=torch.float16, device=dev))
+            mlp_layer_planes(gp, split_planes(Ws[l].detach(), o, i, 1024.0, transpose=True), P, i, o, 2, G[l - 1],
+                             saved_input=acts[l], dyn=dyn, a_has_dyn=True, y_planes=gprev, planes_with_dyn=True)
+            gp = gprev
+        else:
+            mlp_bwd_data_layer(G[l], Ws[l], o, i, acts[l], ACT_RELU, G[l - 1], dyn_scale=dyn)
     dX0 = None
     if need_x0:
         o, i = Ws[0].shape
         dX0 = torch.empty((P, ((i + 3) // 4) * 4), dtype=torch.float32, device=dev)
-        mlp_bwd_data_layer(G[0], Ws[0], o, i, None, ACT_NONE, dX0, dyn_scale=dyn)
+        if planes:
+            mlp_layer_planes(gp, split_planes(Ws[0].detach(), o, i, 1024.0, transpose=True), P, i, o, 0, dX0, dyn=dyn,
+                             a_has_dyn=True)
+        else:
+            mlp_bwd_data_layer(G[0], Ws[0], o, i, None, ACT_NONE, dX0, dyn_scale=dyn)
     dW, db = [None] * n, [None] * n
     if need_w:
         dW, db = mlp_bwd_weight(G, list(acts), [w.shape[0] for w in Ws], [w.shape[1] for w in Ws], None, dyn)
