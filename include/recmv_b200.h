@@ -382,19 +382,8 @@ RECMV_API int recmv_tc_set_acc_gain(int mode, float gain_per_kblock);
  * are refused with RECMV_E_DEVICE.  info may be NULL; clear != 0 resets the record.                        */
 RECMV_API int recmv_check_async_errors(int* info /*host [3]*/, int clear);
 
-/* Diagnostics for the tcgen05 path (used by tools/tc_bringup.py and tools/tc_trace.py): same computation as
- * recmv_sdf_mlp_fwd in a TC mode (passes = 1 or 3), plus status_host[4] = {code, barrier tag, block, 0}
- * of the kernel's bounded mbarrier waits (code 0 = no wait timed out) and, when dbg_out != NULL, the raw
- * fp32 accumulator (before bias) of layer dbg_layer for the first 128 points, [128][512].              */
-RECMV_API int recmv_sdf_mlp_tc_debug(const float* x, const void* packed, const float* pe_w /*host*/,
-                           float* out_sdf, float* out_feat, int64_t P, int passes, int dbg_layer,
-                           float* dbg_out, int* status_host /*host*/,
-                           unsigned long long* trace /*device [4][2][9][16] clock stamps or NULL*/,
-                           recmv_stream_t stream);
-
-/* Diagnostics: tcgen05 issue-rate microbenchmark (cycles per M x N x 16 kind::f16 MMA with smem operands). */
-RECMV_API int recmv_tc_microbench(int cta_group, int M, int N, int iters, int num_ctas, int flags, const void* gsrc,
-                        unsigned long long* out, recmv_stream_t stream);
+/* Diagnostics (tcgen05 bring-up trace entry, issue-rate microbenchmark) are NOT part of this ABI: include/recmv_b200_diag.h,
+ * librecmv_b200_diag.so (tools/ only).                                                                                  */
 
 /* ---- the fused render path (BASELINE north star) -------------------------------------------------
  * One launch: ray r, sample k -> x_obs = cam_pos + t_k dir_r, t_k = t_near + (k+1/2)(t_far-t_near)/S

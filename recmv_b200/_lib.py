@@ -126,10 +126,7 @@ SIGNATURES = {
                                     c_float, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p, c_int64, c_void_p]),
     "recmv_surface_grad_coeffs": (c_int, [c_void_p] * 9 + [c_int64, c_void_p]),
     "recmv_tc_set_acc_gain": (c_int, [c_int, c_float]),
-    "recmv_tc_microbench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "recmv_check_async_errors": (c_int, [POINTER(c_int), c_int]),
-    "recmv_sdf_mlp_tc_debug": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int64,
-                                       c_int, c_int, c_void_p, POINTER(c_int), c_void_p, c_void_p]),
     "recmv_render_sdf": (c_int, [c_void_p, POINTER(RayMarch), c_void_p, c_void_p, c_void_p, c_int64,
                                  c_int, POINTER(Voxel), c_void_p, POINTER(c_float), c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
@@ -137,7 +134,18 @@ SIGNATURES = {
                                     c_void_p]),
 }
 
+# diagnostics (include/recmv_b200_diag.h), not part of the product ABI
+DIAG_SIGNATURES = {
+    "recmv_sdf_mlp_tc_debug": (c_int, [c_void_p, c_void_p, POINTER(c_float), c_void_p, c_void_p, c_int64,
+                                       c_int, c_int, c_void_p, POINTER(c_int), c_void_p, c_void_p]),
+}
+DIAG_LIB_SIGNATURES = {
+    "recmv_tc_microbench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+}
+DIAG_LIB_PATH = os.path.join(_HERE, "librecmv_b200_diag.so")
+
 _lib = None
+_diag = None
 
 
 def load():
@@ -151,12 +159,25 @@ def load():
             "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C recmv_b200/csrc`). "
             "There is no CPU fallback.")
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(DIAG_SIGNATURES.items()):
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def load_diag():
+    """librecmv_b200_diag.so (tools only): the tcgen05 issue-rate microbenchmark."""
+    global _diag
+    if _diag is None:
+        lib = ctypes.CDLL(DIAG_LIB_PATH)
+        for name, (res, args) in DIAG_LIB_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _diag = lib
+    return _diag
 
 
 def check(status, what=""):

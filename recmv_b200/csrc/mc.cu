@@ -53,6 +53,11 @@ __constant__ McTables c_mc;
 // copy of the triangle table in global memory: the face kernel indexes it with per-thread case numbers, and
 // divergent __constant__ reads serialise 32-way (L1-cached global loads do not)
 __device__ signed char g_mc_tri[256][16];
+// ... and so are the per-case counts and the edge-owner table: the emit / count passes index them with per-lane case
+// numbers and edge ids (packed: di | dj << 8 | dk << 16 | axis << 24)
+__device__ unsigned char g_mc_ntri[256];
+__device__ unsigned char g_mc_vinfo[256];
+__device__ unsigned int g_mc_owner[12];
 
 static void build_tables(McTables& t) {
   for (int c = 0; c < 256; ++c) {
@@ -83,6 +88,16 @@ static int ensure_tables() {
     cudaError_t e = cudaMemcpyToSymbol(c_mc, &host, sizeof(McTables));
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpyToSymbol(g_mc_tri, host.tri, sizeof(host.tri));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_mc_ntri, host.ntri, sizeof(host.ntri));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpyToSymbol(g_mc_vinfo, host.vinfo, sizeof(host.vinfo));
+    if (e != cudaSuccess) return (int)e;
+    unsigned int owner[12];
+    for (int q = 0; q < 12; ++q)
+      owner[q] = (unsigned)(host.owner[q][0] & 255) | ((unsigned)(host.owner[q][1] & 255) << 8) |
+                 ((unsigned)(host.owner[q][2] & 255) << 16) | ((unsigned)(host.owner[q][3] & 255) << 24);
+    e = cudaMemcpyToSymbol(g_mc_owner, owner, sizeof(owner));
     if (e != cudaSuccess) return (int)e;
     dev_done[dev] = 1;
   }
@@ -201,7 +216,7 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_count_kernel(const unsigned* 
       int i, j, k;
       if (!cell_coords(b + t, N, NX, NY, NZ, plane, dplane, dnz, i, j, k)) continue;
       const int ci = cube_index(r, t);
-      acc += (c_mc.vinfo[ci] >> 6) | ((int)c_mc.ntri[ci] << 16);
+      acc += (g_mc_vinfo[ci] >> 6) | ((int)g_mc_ntri[ci] << 16);
     }
   }
   const int tot = __reduce_add_sync(0xffffffffu, acc);
@@ -280,7 +295,7 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
       int i, j, k;
       if (!cell_coords(b + t, N, NX, NY, NZ, plane, dplane, dnz, i, j, k)) { r.active &= ~(1u << t); continue; }
       const int ci = cube_index(r, t);
-      mine += kFaces ? (int)c_mc.ntri[ci] : (int)(c_mc.vinfo[ci] >> 6);
+      mine += kFaces ? (int)g_mc_ntri[ci] : (int)(g_mc_vinfo[ci] >> 6);
     }
   }
   int row_total;
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
     cell_coords(idx, N, NX, NY, NZ, plane, dplane, dnz, i, j, k);
     const int ci = cube_index(r, t);
     if (!kFaces) {
-      const int info = c_mc.vinfo[ci];
+      const int info = g_mc_vinfo[ci];
       const int cnt = info >> 6;
       if (cnt == 0) continue;
       const int vbase = off;
@@ -320,14 +335,15 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
       }
       off += cnt;
     } else {
-      const int cnt = c_mc.ntri[ci];
+      const int cnt = g_mc_ntri[ci];
       const long long fbase = off;
       for (int tt = 0; tt < cnt; ++tt) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const int e = g_mc_tri[ci][3 * tt + c];
-          const int oi = i + c_mc.owner[e][0], oj = j + c_mc.owner[e][1], ok = k + c_mc.owner[e][2];
-          const int d = c_mc.owner[e][3];
+          const unsigned ow = g_mc_owner[e];
+          const int oi = i + (int)(ow & 255u), oj = j + (int)((ow >> 8) & 255u), ok = k + (int)((ow >> 16) & 255u);
+          const int d = (int)(ow >> 24);
           long long vid = -1;
           if (oi < NX - 1 && oj < NY - 1 && ok < NZ - 1) {
             const int info = cellinfo[((int64_t)oi * NY + oj) * NZ + ok];

@@ -28,6 +28,7 @@
 // Every mbarrier wait is bounded: a protocol bug surfaces as a status code, not a hung GPU.
 #include "sdf_mlp.cuh"
 #include "tc_common.cuh"
+#include "../../include/recmv_b200_diag.h"   // recmv_sdf_mlp_tc_debug (diagnostics entry, not in the product header)
 
 namespace recmv {
 using namespace tc;
@@ -1188,7 +1189,7 @@ extern "C" int recmv_check_async_errors(int* info, int clear) {
   return RECMV_E_DEVICE;
 }
 
-// Diagnostics entry (see include/recmv_b200.h): runs the tcgen05 path on canonical points and returns
+// Diagnostics entry (see include/recmv_b200_diag.h): runs the tcgen05 path on canonical points and returns
 // the device status record (which bounded wait timed out, if any) plus the raw accumulator of one layer.
 extern "C" int recmv_sdf_mlp_tc_debug(const float* x, const void* packed, const float* pe_w, float* out_sdf,
                                       float* out_feat, int64_t P, int passes, int dbg_layer, float* dbg_out,

@@ -9,7 +9,7 @@
 //  16 commit every K block (4 MMAs)             256 commit every 2 K blocks (8 MMAs)    512 every 3 (12 MMAs)
 //  32 blocking try_wait (completed phase) per K block    64 the same, issued BEFORE the K block's MMAs and
 //     consumed after them (software pipelined)  128 two issuing threads (warps 0 and 2), one accumulator each
-#include "../../include/recmv_b200.h"
+#include "../../include/recmv_b200_diag.h"
 #include "tc_common.cuh"
 
 namespace recmv {

@@ -1,6 +1,8 @@
 """GPU parity of the fused SDF path (PE + 9-layer MLP, and the full ray->sdf render) against the
 golden vectors generated from the reference's own ImplicitNetwork and against the oracle composition.
-Tolerance: BASELINE north star -- 1e-4 relative fp32, metric |a-b| / max(|b|, 1e-2)."""
+Metric: element-wise |a-b| / max(|b|, 1e-2).  The north star's 1e-4 is asserted against the float64 ground truth
+(test_sdf_c1_error_against_fp64_truth: ours <= 1.2e-4 measured 5.6e-5 .. 1.0e-4, the reference's own fp32 3.2e-5 .. 4.5e-5);
+against the reference's fp32 NUMBERS the bound is the triangle inequality 1e-4 + 4.5e-5 -> 1.5e-4 (measured <= 1.09e-4)."""
 import pytest
 import torch
 
@@ -20,7 +22,7 @@ DEV = "cuda:0"
 #    (recmv_tc_set_acc_gain; without it: 9e-5 of the output scale, 7e-4 element-wise).  Measured with the
 #    compensation: 0.9-1.1e-5 of the output scale, 0.9-1.05e-4 element-wise at the 1e-2 floor.
 #  * tc1 is not parity grade (11-bit operands, like the TF32 the reference ran with on Ampere).
-MODES = [("simt", _lib.MLP_FP32_SIMT, 1e-4, 2e-4), ("tc3", _lib.MLP_TC_F16X3, 3e-5, 2.5e-4),
+MODES = [("simt", _lib.MLP_FP32_SIMT, 1e-4, 1.5e-4), ("tc3", _lib.MLP_TC_F16X3, 3e-5, 1.5e-4),
          ("tc1", _lib.MLP_TC_F16X1, 5e-3, 6e-2)]
 
 

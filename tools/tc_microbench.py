@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from recmv_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.load_diag()
 dev = torch.device("cuda", 0)
 out = torch.zeros(8, dtype=torch.int64, device=dev)
 gsrc = torch.randint(0, 255, (148 * 65536 + 65536,), dtype=torch.uint8, device=dev)
