@@ -390,7 +390,11 @@ class LBSkinner(nn.Module):
             return out
         self.last_path = "autograd-composite"
         nps = self.inv_transform_v(tps, self.bbox_extend, self.bbox_center).view(-1, 3)
-        ps_ws = ops.GridSamplerMine3dFunction.apply(self.ws, nps.reshape(1, 1, 1, -1, 3)).view(-1, nps.shape[0]).transpose(0, 1)
+        # the frozen voxel in its cached channels-last layout (one corner = 24 contiguous floats): same kernels, 3-4x the
+        # effective bandwidth of the reference layout (profiles/r02_ref_natives.json)
+        ws_cl = self.ws_channels_last()
+        ps_ws = ops.FrozenVoxelSampleFunction.apply(ws_cl.view(1, *ws_cl.shape), nps.reshape(1, 1, 1, -1, 3))
+        ps_ws = ps_ws.view(-1, nps.shape[0]).transpose(0, 1)
         if batch_inds is None:
             bsz, pnum, _ = ps.shape
             T = torch.matmul(ps_ws.view(bsz, pnum, 24), A.view(batch_size, 24, 16)).view(bsz, pnum, 4, 4)

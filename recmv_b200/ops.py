@@ -200,6 +200,37 @@ class GridSamplerMine3dBackwardFunction(torch.autograd.Function):
         return o0, o1, o2
 
 
+class FrozenVoxelSampleFunction(torch.autograd.Function):
+    """Twice-differentiable trilinear / border sample of a FROZEN channels-last voxel [1,D,H,W,C] (the cached layout of
+    LBSkinner.ws: one corner = C contiguous floats) -- the autograd path of LBSkinner.forward.  Same kernels as
+    GridSamplerMine3dFunction (recmv_gridsample3d_{fwd,bwd,bwd2}) with layout NDHWC; the voxel gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, voxel_cl, grid):
+        grid = grid.contiguous()
+        ctx.save_for_backward(voxel_cl, grid)
+        return grid_sample3d_forward(voxel_cl, grid, LAYOUT_NDHWC)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        voxel_cl, grid = ctx.saved_tensors
+        return None, _FrozenVoxelSampleBackward.apply(voxel_cl, grid, grad_output)
+
+
+class _FrozenVoxelSampleBackward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, voxel_cl, grid, grad_output):
+        ctx.save_for_backward(voxel_cl, grid, grad_output)
+        return grid_sample3d_backward(voxel_cl, grid, grad_output, LAYOUT_NDHWC, need_grad_input=False)[1]
+
+    @staticmethod
+    def backward(ctx, gg_grid):
+        voxel_cl, grid, grad_output = ctx.saved_tensors
+        _, g_grid, gg_out = grid_sample3d_dbackward(None, gg_grid.contiguous(), voxel_cl, grid, grad_output, LAYOUT_NDHWC,
+                                                    need_grad_input=False)
+        return None, g_grid, gg_out
+
+
 def voxel_to_channels_last(ws):
     """[1,C,D,H,W] fp32 -> [D,H,W,C] (private, coalesced copy of LBSkinner.ws)."""
     _check_input(ws, "ws")

@@ -103,7 +103,9 @@ def test_c2f_sweep_and_discretize_on_gpu():
     assert sum(s[3] for s in eng2.stats) < 0.25 * 129 ** 3
 
 
-@pytest.mark.parametrize("resolutions", [[17, 33, 65, 129], [(15, 21, 9), (29, 41, 17), (57, 81, 33), (113, 161, 65)]])
+@pytest.mark.parametrize("resolutions", [[17, 33, 65, 129], [(15, 21, 9), (29, 41, 17), (57, 81, 33), (113, 161, 65)],
+                                         # the full production 'coarse' pyramid of train.py:42-48
+                                         [(15, 21, 9), (29, 41, 17), (57, 81, 33), (113, 161, 65), (225, 321, 129)]])
 def test_c2f_device_worklist_is_bit_identical_to_the_torch_path(resolutions):
     """Seg3dLossless with the sweep as a device worklist (recmv_c2f_compact / recmv_sdf_mlp_fwd_counted /
     recmv_c2f_scatter / recmv_c2f_conflict_todo): same voxels re-queried, same query-point arithmetic -> the grid equals
@@ -111,8 +113,9 @@ def test_c2f_device_worklist_is_bit_identical_to_the_torch_path(resolutions):
     statistics included; isotropic pyramid and the anisotropic 'coarse' pyramid of train.py:42-48 (halved)."""
     from recmv_b200 import testing
     sdf = testing.build_sdf(M.getTmpSdf, seed=0, perturb_seed=101).to(DEV)
-    eng = Seg3dLossless(None, b_min=[-1, -1, -1], b_max=[1, 1, 1], resolutions=resolutions, align_corners=False,
-                        balance_value=0.0).to(DEV)
+    aniso = not isinstance(resolutions[0], int)
+    eng = Seg3dLossless(None, b_min=[-0.7, -1.0, -0.4] if aniso else [-1, -1, -1], b_max=[0.7, 1.0, 0.4] if aniso else [1, 1, 1],
+                        resolutions=resolutions, align_corners=False, balance_value=0.0).to(DEV)
 
     def q(points):
         with torch.no_grad():
