@@ -199,7 +199,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
                              "sample": f"{rays} rays x 64 samples, torch CPU fp32, {threads} threads (fastest of 8/16/32/64)"},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def secondary_rates(dev, ren, mode):
@@ -301,7 +301,28 @@ def secondary_rates(dev, ren, mode):
     }
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line (the JSON).  Libraries print there too (NCCL's "NCCL version ..." banner goes to
+    stdout at NCCL_DEBUG >= VERSION), so the process' fd 1 is pointed at stderr and the JSON line is written to a private
+    duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -330,8 +351,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly ONE line (the JSON): keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO in
-        # some environments) off it unless the caller asks for NCCL logging explicitly through RECMV_NCCL_DEBUG
+        # NCCL logging only when asked for (RECMV_NCCL_DEBUG=INFO shows the NVLS / ring choice); it lands on stderr
         os.environ["NCCL_DEBUG"] = os.environ.get("RECMV_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
@@ -542,7 +562,7 @@ def main():
             mc["roofline"] = {"bound": "hbm", "achieved": mc["algorithmic_bytes"] / (mc["ms_per_call"] * 1e-3) / 1e9,
                               "peak": hbm, "unit": "GB/s",
                               "frac": mc["algorithmic_bytes"] / (mc["ms_per_call"] * 1e-3) / 1e9 / hbm}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
