@@ -382,6 +382,15 @@ RECMV_API int recmv_tc_set_acc_gain(int mode, float gain_per_kblock);
  * are refused with RECMV_E_DEVICE.  info may be NULL; clear != 0 resets the record.                        */
 RECMV_API int recmv_check_async_errors(int* info /*host [3]*/, int clear);
 
+/* ---- (f4) deformation regulariser: 3x3 SVD of the translator Jacobians ---------------------------------------------
+ * replaces `_, s, _ = torch.svd(Jacobs.cpu())` and its autograd backward (engineer/networks/OptimGarmentNetwork.py:1148:
+ * device -> host copy, LAPACK, host -> device copy on every training step).  J [N,3,3] f32 row-major = U diag(S) V^T,
+ * S [N,3] descending (torch.svd's convention); U, V [N,3,3] may be NULL.  One-sided Jacobi in registers, one matrix per
+ * thread.  recmv_svd3x3_backward_s: dJ = U diag(dS) V^T -- the VJP of S alone (what a loss on the singular values needs). */
+RECMV_API int recmv_svd3x3(const float* J, int64_t N, float* U, float* S, float* V, recmv_stream_t stream);
+RECMV_API int recmv_svd3x3_backward_s(const float* U, const float* V, const float* dS, int64_t N, float* dJ,
+                                      recmv_stream_t stream);
+
 /* Diagnostics (tcgen05 bring-up trace entry, issue-rate microbenchmark) are NOT part of this ABI: include/recmv_b200_diag.h,
  * librecmv_b200_diag.so (tools/ only).                                                                                  */
 

@@ -160,8 +160,9 @@ class ImplicitNetwork(nn.Module):
         if y is None:
             y = self.forward(x, None)
         d_output = torch.ones_like(y, requires_grad=False, device=y.device)
-        gradients = torch.autograd.grad(outputs=y, inputs=x, grad_outputs=d_output, create_graph=True,
-                                        retain_graph=True, only_inputs=True)[0]
+        with ops.input_grad_only():   # second order on the tcgen05 GEMMs (recmv_b200/second_order.py)
+            gradients = torch.autograd.grad(outputs=y, inputs=x, grad_outputs=d_output, create_graph=True,
+                                            retain_graph=True, only_inputs=True)[0]
         return gradients.view(-1, 3)
 
 

@@ -466,6 +466,29 @@ ACT_NONE, ACT_SOFTPLUS100, ACT_RELU = 0, 1, 2
 # gradient uses the latter in both settings.
 import os as _os
 TRAIN_GEMM = _os.environ.get("RECMV_TRAIN_GEMM", "planes")
+# create_graph=True input gradients: "1" = differentiable reverse chain on the tcgen05 GEMMs (second_order.py), "0" = torch graph
+SECOND_ORDER_FUSED = _os.environ.get("RECMV_SECOND_ORDER", "1") != "0"
+_INPUT_GRAD_ONLY = [0]
+
+
+class input_grad_only:
+    """`with ops.input_grad_only(): torch.autograd.grad(y, x, ..., create_graph=True)` -- tells the training Functions that
+    this differentiation asks for INPUT gradients only (ctx.needs_input_grad cannot: it reflects requires_grad at forward
+    time, and the parameters always require grad while training).  The mirrors of the reference's call sites use it
+    (ImplicitNetwork.gradient, utils.compute_Jacobian, utils.compute_deformed_normals).  The backward runs on autograd's
+    device thread, so the flag is process-wide, not thread-local (one process drives one GPU)."""
+
+    def __enter__(self):
+        _INPUT_GRAD_ONLY[0] += 1
+        return self
+
+    def __exit__(self, *exc):
+        _INPUT_GRAD_ONLY[0] -= 1
+        return False
+
+
+def _inputs_only(need_params):
+    return SECOND_ORDER_FUSED and (not need_params or _INPUT_GRAD_ONLY[0] > 0)
 _INV_SQRT2 = 0.70710678118654752440
 
 
@@ -670,8 +693,15 @@ class SdfMlpTrainFunction(torch.autograd.Function):
         dev = x.device
         need_x = ctx.needs_input_grad[0]
         need_w = any(ctx.needs_input_grad[4:])
+        if torch.is_grad_enabled() and _inputs_only(need_w):
+            # create_graph=True for the INPUT gradient only (ImplicitNetwork.gradient / deformed normals): the reverse
+            # chain as a differentiable op whose own backward is tangent + backward GEMMs on tcgen05 (second_order.py)
+            from . import second_order
+            SdfMlpTrainFunction.last_backward = "fused-tcgen05 (create_graph, input gradient)"
+            dx = second_order.sdf_input_grad(x, g_sdf, g_feat, ctx.pe_w, act, Ws, bs) if need_x else None
+            return (dx, None, None, None, *([None] * 18))
         if torch.is_grad_enabled():
-            # create_graph=True: differentiate a torch graph of the same network (second order stays on torch)
+            # create_graph=True with parameter gradients in the graph: differentiate a torch graph of the same network
             SdfMlpTrainFunction.last_backward = "autograd-composite (create_graph)"
             xi = x if x.requires_grad else x.detach().requires_grad_(need_x)
             with torch.enable_grad():
@@ -823,6 +853,14 @@ class TranslatorTrainFunction(torch.autograd.Function):
         ps, conds, batch_inds = saved[:3]
         Ws, bs, acts = saved[3:3 + n], saved[3 + n:3 + 2 * n], saved[3 + 2 * n:]
         need = ctx.needs_input_grad
+        if torch.is_grad_enabled() and _inputs_only(any(need[4:])):
+            # utils.compute_Jacobian(..., create_graph=True) of the deformation regulariser: see second_order.py
+            from . import second_order
+            TranslatorTrainFunction.last_backward = "fused-tcgen05 (create_graph, input gradient)"
+            dX0 = second_order.PlainMlpInputGradFunction.apply(g_off.contiguous().float(), n, *acts, *Ws)
+            dps = second_order.pe_vjp_torch(ps, dX0, ctx.pe_w, 6) if need[0] else None
+            dconds = torch.zeros_like(conds).index_add(0, batch_inds, dX0[:, 39:167]) if need[1] else None
+            return (dps, dconds, None, None, *([None] * (2 * n)))
         if torch.is_grad_enabled():
             TranslatorTrainFunction.last_backward = "autograd-composite (create_graph)"
             with torch.enable_grad():
@@ -869,6 +907,15 @@ class RenderNetTrainFunction(torch.autograd.Function):
         points, normals, view_dirs, feats = saved[:4]
         Ws, bs, acts = saved[4:4 + n], saved[4 + n:4 + 2 * n], saved[4 + 2 * n:]
         need = ctx.needs_input_grad
+        if torch.is_grad_enabled() and _inputs_only(any(need[5:])):
+            from . import second_order
+            RenderNetTrainFunction.last_backward = "fused-tcgen05 (create_graph, input gradient)"
+            dX0 = second_order.PlainMlpInputGradFunction.apply(g_out.contiguous().float(), n, *acts, *Ws)
+            dp = dX0[:, 0:3] if need[0] else None
+            dn = dX0[:, 30:33] if need[1] else None
+            dv = second_order.pe_vjp_torch(view_dirs, dX0[:, 3:30], ctx.pe_w, 4) if need[2] else None
+            df = dX0[:, 33:289] if need[3] else None
+            return (dp, dn, dv, df, None, *([None] * (2 * n)))
         if torch.is_grad_enabled():
             RenderNetTrainFunction.last_backward = "autograd-composite (create_graph)"
             with torch.enable_grad():
@@ -1225,6 +1272,49 @@ def surface_grad_coeffs(grad_l_p, grad_f_p, jac, rays, d_minus_c=None):
         check(_lib.load().recmv_surface_grad_coeffs(*[_ptr(a) for a in args], _ptr(dc), _ptr(coef), _ptr(vec), _ptr(rg),
                                                     _ptr(ok), n, _stream(coef)), "recmv_surface_grad_coeffs")
     return coef, vec, rg, ok.view(torch.bool)
+
+
+class Svd3x3Function(torch.autograd.Function):
+    """(U, S, V) = svd(J), J [N,3,3] float32 CUDA, J = U diag(S) V^T with S descending -- torch.svd's contract, computed
+    per matrix in registers (csrc/svd3.cu) instead of the reference's round trip through the host
+    (`torch.svd(Jacobs.cpu())`, engineer/networks/OptimGarmentNetwork.py:1148).  Differentiable through S (dJ = U diag(dS)
+    V^T, one launch); a cotangent on U or V raises (the reference's loss reads the singular values only)."""
+
+    @staticmethod
+    def forward(ctx, J):
+        _check_input(J, "J")
+        if J.dtype != torch.float32 or J.dim() != 3 or tuple(J.shape[1:]) != (3, 3):
+            raise TypeError("svd3x3 expects a float32 [N,3,3] tensor")
+        N = J.shape[0]
+        U = torch.empty((N, 3, 3), dtype=torch.float32, device=J.device)
+        V = torch.empty((N, 3, 3), dtype=torch.float32, device=J.device)
+        S = torch.empty((N, 3), dtype=torch.float32, device=J.device)
+        with torch.cuda.device(J.device):
+            check(_lib.load().recmv_svd3x3(_ptr(J), N, _ptr(U), _ptr(S), _ptr(V), _stream(J)), "recmv_svd3x3")
+        ctx.save_for_backward(U, V)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(U, V)
+        return U, S, V
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gU, gS, gV):
+        if gU is not None or gV is not None:
+            raise NotImplementedError("svd3x3 is differentiable through the singular values only")
+        if gS is None:
+            return None
+        U, V = ctx.saved_tensors
+        gS = gS.contiguous().float()
+        dJ = torch.empty_like(U)
+        with torch.cuda.device(U.device):
+            check(_lib.load().recmv_svd3x3_backward_s(_ptr(U), _ptr(V), _ptr(gS), U.shape[0], _ptr(dJ), _stream(U)),
+                  "recmv_svd3x3_backward_s")
+        return dJ
+
+
+def svd3x3(J):
+    """torch.svd for a batch of 3x3 matrices on the device: returns (U, S, V)."""
+    return Svd3x3Function.apply(J.contiguous())
 
 
 def check_async_errors(clear=False):

@@ -2,6 +2,7 @@
 198-264).  Same names, arguments and return values; the native calls go to librecmv_b200.so."""
 import torch
 
+from .. import ops as _ops
 from ..model.Embedder import annealing_weights  # noqa: F401  (utils/utils.py:40-46)
 from ..ops import FastDiff3x3MinvFunction  # noqa: F401    (utils/utils.py:8-18)
 from . import FindSurfacePs as _fsp
@@ -15,8 +16,9 @@ def compute_Jacobian(ps, ds, retain_graph, create_graph, allow_unused=False):
     go = torch.ones_like(ds[..., 0])
     for i in range(3):
         keep = True if i < 2 else retain_graph
-        g = torch.autograd.grad(ds[..., i], ps, go, retain_graph=keep, create_graph=create_graph,
-                                allow_unused=allow_unused)
+        with _ops.input_grad_only():   # only d/d ps is asked for: create_graph stays on the tcgen05 GEMMs
+            g = torch.autograd.grad(ds[..., i], ps, go, retain_graph=keep, create_graph=create_graph,
+                                    allow_unused=allow_unused)
         rows.append(g[0].view(-1, 1, 3))
     return torch.cat(rows, dim=1)
 
@@ -58,7 +60,8 @@ def compute_deformed_normals(sdf, deformer, ps, defconds, batch_inds, ratio, pha
     """n = normalize(J^-T grad sdf) (utils/utils.py:198-230)."""
     sdfs = sdf(ps, ratio)
     check = phase in ('train', 'Train')
-    onx = torch.autograd.grad(sdfs, ps, torch.ones_like(sdfs), retain_graph=check, create_graph=check)[0]
+    with _ops.input_grad_only():
+        onx = torch.autograd.grad(sdfs, ps, torch.ones_like(sdfs), retain_graph=check, create_graph=check)[0]
     ds, J = _value_and_jacobian(deformer, ps, defconds, batch_inds, ratio, offset_type, check)
     Jinv, ok = FastDiff3x3MinvFunction.apply(J)
     nx = Jinv.transpose(-2, -1).matmul(onx.view(-1, 3, 1)).view(-1, 3)
@@ -92,3 +95,33 @@ def implicit_surface_grad_coeffs(sdf, deformer, ps, rays, grad_l_p, defconds, ba
         dc = (d - cam_pos.view(1, 3)) if cam_pos is not None else None
         coef, vec, rg, ok = ops.surface_grad_coeffs(grad_l_p, gf, J, rays, dc)
     return coef, vec, rg, ok, d
+
+
+def GMRobustError(x, c, square=False):
+    """Geman-McClure robust error (utils/utils.py:48-52)."""
+    if square:
+        return 2. * x / (c * c) / (x / (c * c) + 4)
+    return 2. * x * x / (c * c) / (x * x / (c * c) + 4)
+
+
+def eikonal_loss(sdf, pnts, ratio):
+    """The eikonal term of the training step (engineer/networks/OptimGarmentNetwork.py:1108-1118;
+    OptimNetwork.py's human branch is the same three lines): ((|grad_x sdf| - 1)^2).mean().
+    `sdf.gradient` differentiates with create_graph=True; with the fused training path both that reverse chain and the
+    backward of THIS loss run on the tcgen05 GEMMs (recmv_b200/second_order.py)."""
+    pnts.requires_grad_()
+    pred = sdf(pnts, ratio)
+    grad = sdf.gradient(pnts, pred)
+    return ((grad.norm(2, dim=-1) - 1) ** 2).mean()
+
+
+def deformation_regulariser(translator, pnts, d_cond, ratio, c, offset_type=None):
+    """The deformation regulariser (OptimGarmentNetwork.py:1135-1154): Jacobian of the canonical-space deformation by
+    three create_graph passes, its singular values, log, Geman-McClure on sum(log^2 s).  The reference copies the
+    Jacobians to the host for `torch.svd`; here they stay on the device (ops.svd3x3, csrc/svd3.cu)."""
+    pnts.requires_grad_()
+    defVs = translator(pnts, d_cond, ratio=ratio, offset_type=offset_type)
+    Jacobs = compute_Jacobian(pnts, defVs, True, True)
+    _, s, _ = _ops.svd3x3(Jacobs)
+    s = torch.log(s)
+    return GMRobustError((s * s).sum(1), c, True).mean()
