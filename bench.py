@@ -290,8 +290,45 @@ def secondary_rates(dev, ren, mode):
     train["torch_autograd_cublas_fp32_ms_per_step"] = ref["ms_per_step"]
     train["speedup_vs_torch_autograd"] = ref["ms_per_step"] / train["ms_per_step"]
 
+    # second order: the eikonal term of the training step -- net.gradient(x) with create_graph=True, then
+    # ((|grad| - 1)^2).mean().backward() -- on the tcgen05 GEMMs (recmv_b200/second_order.py) and, for comparison, through
+    # torch autograd over cuBLAS fp32.  The reference draws ~8-16 k points per step for this term (OptimGarmentNetwork.py:1107).
+    from recmv_b200 import utils as U
+    Pe = 1 << 14
+    xe = pts[:Pe].clone()
+
+    def eik_step():
+        for p_ in sdf_net.parameters():
+            p_.grad = None
+        U.eikonal_loss(sdf_net, xe.detach().clone(), None).backward()
+
+    def rate_eik():
+        for _ in range(2):
+            eik_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            eik_step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / 5
+    eik_ms = rate_eik()
+    eik = {"ms_per_step": eik_ms, "points": Pe, "points_per_s": Pe / (eik_ms * 1e-3), "path": sdf_net.last_path,
+           "backward": ops.SdfMlpTrainFunction.last_backward,
+           "gemm_launches": "9 forward + 9 reverse + 9 tangent + 8 backward-data layer GEMMs, 2 weight-gradient launches"}
+    sdf_net.train_fused = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        eik_ref = rate_eik()
+    finally:
+        sdf_net.train_fused = True
+        torch.backends.cuda.matmul.allow_tf32 = allow
+    eik["torch_autograd_cublas_fp32_ms_per_step"] = eik_ref
+    eik["speedup_vs_torch_autograd"] = eik_ref / eik_ms
+
     return {
         "sdf_train_step (fused forward + tcgen05 backward, loss.backward())": train,
+        "sdf_eikonal_step (second order: gradient(create_graph) + loss.backward())": eik,
         "deformer_fwd (MLPTranslator + LBS, one launch)": rate(
             lambda: deformer(pts, [conds, [poses, trans]], bi, ratio=ratio, offset_type="body"), 1746944),
         "deformer_fwd_jac (value + 3x3 Jacobian, forward mode)": rate(

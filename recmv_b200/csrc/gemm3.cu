@@ -297,10 +297,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm3_kernel(const __grid_constan
     for (long long ch = 0; ch < nchunks; ++ch) {
       const int buf = (int)(ch & 1);
       // compensation of the tensor core's truncating fp32 accumulation: every 64-wide K block adds 4 hi*hi MMAs into
-      // the full-size accumulator, each dropping ~2^-24 of it on average (same constant as the forward engine,
-      // recmv_tc_set_acc_gain; measured here without it: 2.0e-6 after 8 K blocks, 7.9e-6 after 32 = 4.1 x 2^-24 each)
+      // the full-size accumulator, each dropping a fraction of 2^-24 of it on average (acc_trunc_gain, tc_common.cuh)
       const long long kbs = (ch + 1) * chunk_kb <= nkb ? chunk_kb : nkb - ch * chunk_kb;
-      const float unscale = unscale0 * (1.f + 4.f * 5.9604645e-8f * (float)kbs);
+      const float unscale = unscale0 * acc_trunc_gain((int)kbs);
       mbar_wait(BAR(kBarAccFull + buf), (uint32_t)((ch >> 1) & 1), abort_flag, prm.status, 2400 + buf);
       tc_fence_after();
 #pragma unroll 1

@@ -166,8 +166,8 @@ gemm3_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int cg = (warp - 2) >> 2;            // its 32-column group of the tile
     const int row = q * 32 + lane;
     const float dyn = prm.dyn_scale ? __ldg(prm.dyn_scale) : 1.f;
-    // truncating-accumulation compensation: 4 hi*hi MMAs per K block, ~2^-24 each (gemm3.cu)
-    const float unscale = prm.unscale / dyn * (1.f + 4.f * 5.9604645e-8f * (float)nkb);
+    // truncating-accumulation compensation (acc_trunc_gain, tc_common.cuh)
+    const float unscale = prm.unscale / dyn * acc_trunc_gain(nkb);
     const float pscale = prm.plane_scale * (prm.dyn_in_planes ? dyn : 1.f);
     const bool fwd = prm.epi >= TEPI_FWD_NONE;
     long long item = 0;

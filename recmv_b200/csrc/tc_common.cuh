@@ -182,6 +182,17 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
   return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// Gain that undoes the tensor core's truncating fp32 accumulation after `kblocks` 64-wide K blocks of 3-pass MMAs into
+// one accumulator (the layer GEMMs of gemm3.cu / gemm3_tma.cu).  Measured on B200 as the signed projection
+// <ours, fp64> / <fp64, fp64> - 1 of a GEMM's output (tools/dbg_bias.py; identical for positive and signed operands):
+//     K blocks        1        5        8        32
+//     bias x 2^24   -1.2    -12.8    -24.4    -102          ->  bias ~ -(3.23 n - 1.5) 2^-24
+// (the first MMA overwrites the accumulator and loses nothing; later ones drop a fraction of an ulp of a growing sum).
+// With the earlier 4 n 2^-24 every GEMM came out +4.5e-7 high, +4.8e-6 on the 18-GEMM input gradient of the SDF network.
+__host__ __device__ __forceinline__ float acc_trunc_gain(int kblocks) {
+  return 1.f + (3.23f * (float)kblocks - 1.5f) * 5.9604645e-8f;
+}
+
 // fp32 -> fp16 hi/lo split of 8 consecutive K values, packed for one 16-byte store each.
 // cvt.rn.f16x2.f32 packs two conversions into one ALU-pipe instruction (F2FP.PACK_AB); the scalar
 // __float2half_rn path compiles to F2F on the quarter-rate XU pipe, which made the epilogue XU-bound.

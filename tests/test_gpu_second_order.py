@@ -44,13 +44,14 @@ def test_eikonal_term_matches_reference_double_backward(tag, pseed):
     worst = max(a for _, a, _ in rows)
     print(f"eikonal[{tag}] worst {worst:.2e}")
     for n, a, b in rows:
-        assert a < (5e-4 if n.endswith("sum") else 1e-4), table
+        # measured: loss 5.8e-6, entries <= 1.7e-5, row / column sums <= 1.7e-4 (the reference's fp32: 5.6e-7 / 1.5e-6 / 1.7e-5)
+        assert a < (5e-4 if n.endswith("sum") else 5e-5), (n, a)
     # the same loss through the all-torch module (cuBLAS fp32): same answer, other path
     net.train_fused = False
     net.zero_grad()
     x2 = torch.from_numpy(g["x"]).to(DEV)
     l2 = utils.eikonal_loss(net, x2, {'sdfRatio': 0.7})
-    assert net.last_path == "autograd-composite" and abs(float(l2) - float(loss)) < 1e-5 * float(loss) + 1e-9
+    assert net.last_path == "autograd-composite" and abs(float(l2) - float(loss)) < 1e-4 * float(loss)
     net.train_fused = True
 
 
@@ -104,9 +105,8 @@ def test_svd3x3_matches_lapack_and_its_gradient():
     e = (Jd.grad.cpu().double()[sel][ok] - Jr.grad[sel][ok]).abs().amax(dim=(1, 2)) / Jr.grad[sel][ok].abs().amax(dim=(1, 2))
     print("svd3x3 backward: worst relative error", float(e.max()), "over", int(ok.sum()), "matrices")
     assert float(e.max()) < 2e-4
-    with pytest.raises(NotImplementedError):
-        U2, S2, V2 = ops.svd3x3(Jd)
-        U2.sum().backward()
+    U2, S2, V2 = ops.svd3x3(Jd)
+    assert S2.requires_grad and not U2.requires_grad and not V2.requires_grad   # differentiable through S only
 
 
 def test_deformation_regulariser_matches_reference():
@@ -135,7 +135,9 @@ def test_deformation_regulariser_matches_reference():
     rows = [("loss", abs(float(loss) - float(g["loss_f64"])) / float(g["loss_f64"]),
              abs(float(g["loss_f32"]) - float(g["loss_f64"])) / float(g["loss_f64"])),
             ("dp", merr(pr.grad, g["dp_f64"]), merr(g["dp_f32"], g["dp_f64"])),
-            ("dconds", merr(conds.grad, g["dconds_f64"]), merr(g["dconds_f32"], g["dconds_f64"]))]
+            # the Jacobian depends on the condition only through the ReLU masks: the reference gets exact zeros, the fused
+            # path never creates the gradient
+            ("dconds", 0.0 if conds.grad is None else float(conds.grad.abs().max()), float(np.abs(g["dconds_f32"]).max()))]
     named = [(n, q) for n, q in sorted(tr.named_parameters()) if q.grad is not None]
     rows += _grad_rows("", named, g)
     table = "\n".join(f"def_regu/{n}: |ours-f64| {a:.2e}  |ref32-f64| {b:.2e}" for n, a, b in rows)
@@ -150,10 +152,12 @@ def test_deformation_regulariser_matches_reference():
     l2 = utils.deformation_regulariser(tr, p2, c2, ratio, float(g["c"]), offset_type="body")
     l2.backward()
     assert tr.last_path == "autograd-composite"
-    rows2 = [("dp", merr(p2.grad, g["dp_f64"])), ("dconds", merr(c2.grad, g["dconds_f64"]))]
+    rows2 = [("dp", merr(p2.grad, g["dp_f64"]))]
     rows2 += [(n, a) for n, a, _ in _grad_rows("", [(n, q) for n, q in sorted(tr.named_parameters()) if q.grad is not None], g)]
     print("def_regu, all-torch fp32 on this GPU: " + ", ".join(f"{n} {a:.1e}" for n, a in rows2))
     tr.train_fused = True
+    # measured: loss 1.9e-5 (reference fp32 2.3e-5), dp 1.5e-4 (2.6e-4), weights <= 1.0e-4 (4.6e-5); all-torch fp32 on this
+    # GPU: dp 2.0e-4, weights <= 1.0e-4
     assert rows[0][1] < 1e-4, table
     for n, a, b in rows[1:]:
-        assert a < 5e-3, table
+        assert a < 5e-4, table
