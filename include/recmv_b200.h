@@ -223,6 +223,19 @@ RECMV_API int recmv_mlp_layer_planes(const void* a_hi, const void* a_lo, int64_t
                            int64_t ldy, float* Y2, int64_t ldy2, void* y_hi, void* y_lo, int64_t ldyp, int planes_with_dyn,
                            recmv_stream_t stream);
 
+/* (f4) element-wise steps of the second-order pass between two plane GEMMs (recmv_b200/second_order.py), each one launch that
+ * also writes the next GEMM's A planes (scaled plane_scale [x *scale_dev]):
+ *   softplus_tangent: u = s tz (fp32 + planes), inj = 100 (1 - s) h tz,  s = 1 - exp(-100 a)  (softplus_100' from the saved
+ *                     output a; h = first-order cotangent at the same pre-activation)
+ *   add_split:        y += addend (in place), planes of y                                                                   */
+RECMV_API int recmv_softplus_tangent_planes(const float* tz, int64_t ldt, const float* a, int64_t lda, const float* h,
+                                            int64_t ldh, int64_t rows, int cols, float plane_scale, float* u, int64_t ldu,
+                                            void* u_hi, void* u_lo, int64_t ldp, float* inj, int64_t ldi,
+                                            recmv_stream_t stream);
+RECMV_API int recmv_add_split_planes(float* y, int64_t ldy, const float* addend, int64_t lda, int64_t rows, int cols,
+                                     float scale, const float* scale_dev, void* y_hi, void* y_lo, int64_t ldp,
+                                     recmv_stream_t stream);
+
 /* ---- A3: sdf and its input gradient (ImplicitNetwork.gradient, model/network.py:121-133; the
  * autograd.grad(sdf, p) of utils/FindSurfacePs.py:176 and OptimGarmentNetwork.py:1171,3192) --------------
  * One forward-mode launch of the tcgen05 kernel: every point occupies four tile rows (value and the three

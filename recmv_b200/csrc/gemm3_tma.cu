@@ -277,6 +277,54 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
 }
 
+// Second-order helpers (recmv_b200/second_order.py): the element-wise step between two layer GEMMs of the tangent pass and of
+// the downward pass, each ONE launch that also writes the next GEMM's operand planes.
+//   softplus_tangent: tz = raw tangent of z_l, a = softplus_100(z_l) (saved), h = first-order cotangent at z_l
+//       u   = s tz                 (tangent of a_{l+1};  s = softplus' = 1 - exp(-100 a))      -> fp32 + planes
+//       inj = 100 (1 - s) h tz     (softplus'' u_{l+1} tz: what the second differentiation adds to the cotangent of z_l)
+//   add_split: y += addend, planes of y
+__global__ void __launch_bounds__(256) softplus_tangent_kernel(const float* __restrict__ tz, long long ldt, const float* __restrict__ a,
+                                                               long long lda, const float* __restrict__ h, long long ldh,
+                                                               long long R, int C, float plane_scale, float* __restrict__ u,
+                                                               long long ldu, __half* __restrict__ uh, __half* __restrict__ ul,
+                                                               long long ldp, float* __restrict__ inj, long long ldi,
+                                                               DevStatus* status) {
+  const long long total = R * (long long)C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    const float t = __ldg(tz + r * ldt + c);
+    const float em = expm1f(-100.f * __ldg(a + r * lda + c));      // -s, accurate where s is small
+    const float uv = -em * t;
+    u[r * ldu + c] = uv;
+    inj[r * ldi + c] = 100.f * (1.f + em) * __ldg(h + r * ldh + c) * t;
+    float v = uv * plane_scale;
+    if (!(fabsf(v) < 65504.f)) { report_range(status, 3700); v = fminf(fmaxf(v, -65504.f), 65504.f); }
+    const __half hh = __float2half_rn(v);
+    uh[r * ldp + c] = hh;
+    ul[r * ldp + c] = __float2half_rn(v - __half2float(hh));
+  }
+}
+
+__global__ void __launch_bounds__(256) add_split_kernel(float* __restrict__ y, long long ldy, const float* __restrict__ addend,
+                                                        long long lda, long long R, int C, float scale,
+                                                        const float* __restrict__ scale_dev, __half* __restrict__ yh,
+                                                        __half* __restrict__ yl, long long ldp, DevStatus* status) {
+  const float s = scale * (scale_dev ? __ldg(scale_dev) : 1.f);
+  const long long total = R * (long long)C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    const float o = y[r * ldy + c] + __ldg(addend + r * lda + c);
+    y[r * ldy + c] = o;
+    float v = o * s;
+    if (!(fabsf(v) < 65504.f)) { report_range(status, 3710); v = fminf(fmaxf(v, -65504.f), 65504.f); }
+    const __half hh = __float2half_rn(v);
+    yh[r * ldp + c] = hh;
+    yl[r * ldp + c] = __float2half_rn(v - __half2float(hh));
+  }
+}
+
 // positional encoding as a saved layer input AND as operand planes
 __global__ void __launch_bounds__(256) pe_forward_planes_kernel(const float* __restrict__ x, PeWeights pw, int bands,
                                                                 float* __restrict__ out, long long ld, __half* __restrict__ oh,
@@ -332,6 +380,35 @@ extern "C" int recmv_split_planes(const float* in, int64_t ld, int64_t R, int C,
   if (s0) return s0;
   split_planes_kernel<<<stride_grid(R * (int64_t)C, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       in, ld, R, C, scale, scale_dev, transpose, (__half*)hi, (__half*)lo, ldp, (DevStatus*)sd);
+  return launch_status();
+}
+
+extern "C" int recmv_softplus_tangent_planes(const float* tz, int64_t ldt, const float* a, int64_t lda, const float* h,
+                                            int64_t ldh, int64_t rows, int cols, float plane_scale, float* u, int64_t ldu,
+                                            void* u_hi, void* u_lo, int64_t ldp, float* inj, int64_t ldi,
+                                            recmv_stream_t stream) {
+  if (rows < 0 || cols <= 0) return RECMV_E_SHAPE;
+  if (rows == 0) return RECMV_OK;
+  if (!tz || !a || !h || !u || !u_hi || !u_lo || !inj) return RECMV_E_NULL;
+  void* sd = nullptr;
+  int s0 = device_status_record(&sd);
+  if (s0) return s0;
+  softplus_tangent_kernel<<<stride_grid(rows * (int64_t)cols, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      tz, ldt, a, lda, h, ldh, rows, cols, plane_scale, u, ldu, (__half*)u_hi, (__half*)u_lo, ldp, inj, ldi, (DevStatus*)sd);
+  return launch_status();
+}
+
+extern "C" int recmv_add_split_planes(float* y, int64_t ldy, const float* addend, int64_t lda, int64_t rows, int cols,
+                                      float scale, const float* scale_dev, void* y_hi, void* y_lo, int64_t ldp,
+                                      recmv_stream_t stream) {
+  if (rows < 0 || cols <= 0) return RECMV_E_SHAPE;
+  if (rows == 0) return RECMV_OK;
+  if (!y || !addend || !y_hi || !y_lo) return RECMV_E_NULL;
+  void* sd = nullptr;
+  int s0 = device_status_record(&sd);
+  if (s0) return s0;
+  add_split_kernel<<<stride_grid(rows * (int64_t)cols, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      y, ldy, addend, lda, rows, cols, scale, scale_dev, (__half*)y_hi, (__half*)y_lo, ldp, (DevStatus*)sd);
   return launch_status();
 }
 

@@ -571,6 +571,25 @@ def split_planes(t, rows, cols, scale, scale_dev=None, transpose=False, ldp=None
     return hi, lo
 
 
+def weight_planes(W, transpose=False):
+    """Operand planes of a layer's weight matrix ([out][in], scale 1024; transpose=True: [in][out], the backward-data
+    operand), computed once per tensor OBJECT and version: the forward, the reverse chain and the two second-order passes of
+    one training step all see the same weight tensor, so three of four splits are cache hits.  The cache lives on the tensor
+    (an attribute), so it dies with it -- no address-keyed table that could go stale."""
+    ver = W._version
+    cache = getattr(W, "_recmv_planes", None)
+    if cache is None or cache[0] != ver:
+        cache = (ver, {})
+        try:
+            W._recmv_planes = cache
+        except AttributeError:
+            pass
+    if transpose not in cache[1]:
+        Wd = W.detach().contiguous().float()
+        cache[1][transpose] = split_planes(Wd, Wd.shape[0], Wd.shape[1], 1024.0, transpose=transpose)
+    return cache[1][transpose]
+
+
 def pe_forward_planes(x, pe_w, bands, out, out_hi, out_lo):
     w = (c_float * (2 * bands))(*[float(v) for v in pe_w[:2 * bands]])
     with torch.cuda.device(x.device):
@@ -593,6 +612,24 @@ def mlp_layer_planes(a_planes, b_planes, M, N, K, mode, Y, bias=None, saved_inpu
             1 if a_has_dyn else 0, int(split), _ptr(Y), Y.stride(0), _ptr(Y2), Y2.stride(0) if Y2 is not None else 0, _ptr(yh),
             _ptr(yl), yh.stride(0) if yh is not None else 0, 1 if planes_with_dyn else 0, _stream(Y)), "recmv_mlp_layer_planes")
     return Y
+
+
+def softplus_tangent_planes(tz, a, h, cols, u, u_planes, inj, plane_scale=64.0):
+    """u[:, :cols] = softplus_100'(z) * tz (+ planes), inj[:, :cols] = softplus_100''(z) * (h / softplus') * tz, from the saved
+    softplus output a (second_order.py's tangent pass; one launch)."""
+    with torch.cuda.device(tz.device):
+        check(_lib.load().recmv_softplus_tangent_planes(
+            _ptr(tz), tz.stride(0), _ptr(a), a.stride(0), _ptr(h), h.stride(0), tz.shape[0], int(cols), float(plane_scale), _ptr(u),
+            u.stride(0), _ptr(u_planes[0]), _ptr(u_planes[1]), u_planes[0].stride(0), _ptr(inj), inj.stride(0), _stream(tz)),
+            "recmv_softplus_tangent_planes")
+
+
+def add_split_planes(y, addend, cols, y_planes, scale=64.0, scale_dev=None):
+    """y[:, :cols] += addend[:, :cols] in place, and the planes of the sum scaled scale (* scale_dev)."""
+    with torch.cuda.device(y.device):
+        check(_lib.load().recmv_add_split_planes(_ptr(y), y.stride(0), _ptr(addend), addend.stride(0), y.shape[0], int(cols),
+                                                 float(scale), _ptr(scale_dev), _ptr(y_planes[0]), _ptr(y_planes[1]),
+                                                 y_planes[0].stride(0), _stream(y)), "recmv_add_split_planes")
 
 
 def pe_backward(x, g, g2, pe_w, bands, dx=None):
@@ -649,6 +686,7 @@ class SdfMlpTrainFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, pe_w, mode, packed, *Wb):
         Ws, bs = Wb[:9], Wb[9:]
+        W_in = Ws
         if not (x.is_contiguous() and x.dtype == torch.float32 and x.dim() == 2):
             raise RuntimeError("SdfMlpTrainFunction expects a contiguous float32 [P,3] tensor (convert outside, in the graph)")
         P = x.shape[0]
@@ -669,7 +707,7 @@ class SdfMlpTrainFunction(torch.autograd.Function):
             pe_forward_planes(x, pe_w, 6, act[4][:, 473:], xp[4][0][:, 473:], xp[4][1][:, 473:])
             for l in range(9):
                 o, i = Ws[l].shape
-                wp = split_planes(Ws[l], o, i, 1024.0)
+                wp = weight_planes(W_in[l])
                 if l < 8:
                     mlp_layer_planes(xp[l], wp, P, o, i, 5, act[l + 1], bias=bs[l], scale=_INV_SQRT2 if l == 4 else 1.0,
                                      y_planes=xp[l + 1])
@@ -732,15 +770,14 @@ class SdfMlpTrainFunction(torch.autograd.Function):
             for l in range(8, 0, -1):
                 G[l - 1] = torch.empty((P, 512), dtype=torch.float32, device=dev)
                 gprev = (torch.empty((P, 512), dtype=torch.float16, device=dev), torch.empty((P, 512), dtype=torch.float16, device=dev))
-                wtp = split_planes(Ws[l].detach(), outs[l], ins[l], 1024.0, transpose=True)     # [in][out]: B of backward-data
+                wtp = weight_planes(Ws[l], transpose=True)                                     # [in][out]: B of backward-data
                 mlp_layer_planes(gp, wtp, P, ins[l], outs[l], 1, G[l - 1], saved_input=act[l], scale=_INV_SQRT2 if l == 4 else 1.0,
                                  dyn=dyn, a_has_dyn=True, split=473 if l == 4 else 0, Y2=dpe4 if l == 4 else None,
                                  y_planes=gprev, planes_with_dyn=True)
                 gp = gprev
             if need_x:
                 dpe0 = torch.empty((P, 40), dtype=torch.float32, device=dev)
-                wtp = split_planes(Ws[0].detach(), outs[0], ins[0], 1024.0, transpose=True)
-                mlp_layer_planes(gp, wtp, P, ins[0], outs[0], 0, dpe0, dyn=dyn, a_has_dyn=True)
+                mlp_layer_planes(gp, weight_planes(Ws[0], transpose=True), P, ins[0], outs[0], 0, dpe0, dyn=dyn, a_has_dyn=True)
                 dx = pe_backward(x, dpe0, dpe4, ctx.pe_w, 6)
         else:
             for l in range(8, 0, -1):

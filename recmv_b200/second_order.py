@@ -24,7 +24,7 @@ import torch
 
 from . import ops
 from .ops import (ACT_NONE, ACT_RELU, ACT_SOFTPLUS100, _INV_SQRT2, grad_dyn_scale, mlp_bwd_data_layer, mlp_bwd_weight,
-                  mlp_fwd_layer, pe_backward)
+                  mlp_fwd_layer, mlp_layer_planes, pe_backward, split_planes)
 
 
 def pe_vjp_torch(x, u, pe_w, bands):
@@ -36,10 +36,6 @@ def pe_vjp_torch(x, u, pe_w, bands):
         out = out + (pe_w[2 * k] * f) * torch.cos(x * f) * u[:, c:c + 3] - (pe_w[2 * k + 1] * f) * torch.sin(x * f) * u[:, c + 3:c + 6]
         f *= 2.0
     return out
-
-
-def _scaled(t, s):
-    return t * s
 
 
 class SdfMlpPeGradFunction(torch.autograd.Function):
@@ -63,12 +59,24 @@ class SdfMlpPeGradFunction(torch.autograd.Function):
         G = [None] * 9
         G[8] = G8
         dpe4 = torch.zeros((P, 40), dtype=torch.float32, device=dev)
-        for l in range(8, 0, -1):
-            G[l - 1] = torch.zeros((P, 512), dtype=torch.float32, device=dev)
-            mlp_bwd_data_layer(G[l], Wd[l], outs[l], ins[l], act[l], ACT_SOFTPLUS100, G[l - 1], split=473 if l == 4 else 0,
-                               D2=dpe4 if l == 4 else None, out_scale=_INV_SQRT2 if l == 4 else 1.0, dyn_scale=dyn)
         dpe0 = torch.zeros((P, 40), dtype=torch.float32, device=dev)
-        mlp_bwd_data_layer(G[0], Wd[0], outs[0], ins[0], None, ACT_NONE, dpe0, dyn_scale=dyn)
+        if ops.TRAIN_GEMM == "planes":
+            gp = split_planes(G8, P, 257, 64.0, scale_dev=dyn, ldp=264)
+            for l in range(8, 0, -1):
+                G[l - 1] = torch.zeros((P, 512), dtype=torch.float32, device=dev)
+                gprev = _plane_pair(P, 512, dev)
+                mlp_layer_planes(gp, ops.weight_planes(Ws[l], transpose=True), P, ins[l], outs[l], 1, G[l - 1],
+                                 saved_input=act[l], scale=_INV_SQRT2 if l == 4 else 1.0, dyn=dyn, a_has_dyn=True,
+                                 split=473 if l == 4 else 0, Y2=dpe4 if l == 4 else None, y_planes=gprev, planes_with_dyn=True)
+                gp = gprev
+            mlp_layer_planes(gp, ops.weight_planes(Ws[0], transpose=True), P, ins[0], outs[0], 0, dpe0,
+                             dyn=dyn, a_has_dyn=True)
+        else:
+            for l in range(8, 0, -1):
+                G[l - 1] = torch.zeros((P, 512), dtype=torch.float32, device=dev)
+                mlp_bwd_data_layer(G[l], Wd[l], outs[l], ins[l], act[l], ACT_SOFTPLUS100, G[l - 1], split=473 if l == 4 else 0,
+                                   D2=dpe4 if l == 4 else None, out_scale=_INV_SQRT2 if l == 4 else 1.0, dyn_scale=dyn)
+            mlp_bwd_data_layer(G[0], Wd[0], outs[0], ins[0], None, ACT_NONE, dpe0, dyn_scale=dyn)
         ctx.pe_w = [float(w) for w in pe_w]
         ctx.dims = (outs, ins)
         ctx.save_for_backward(x, dyn, *act, *Ws, *G)
@@ -88,6 +96,8 @@ class SdfMlpPeGradFunction(torch.autograd.Function):
         Wd = [w.detach().contiguous().float() for w in Ws]
         dq = grad_dyn_scale(q)
         inv_dq = 1.0 / dq
+        if ops.TRAIN_GEMM == "planes":
+            return SdfMlpPeGradFunction._backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, need_g, need_w, dq, inv_dq)
         # ---- upward: tangent pass with tangent of PE = q (scaled into [1,2) by dq; everything below is linear in it) ----
         U = [torch.zeros((P, 64), dtype=torch.float32, device=dev)] + \
             [torch.zeros((P, 512), dtype=torch.float32, device=dev) for _ in range(8)]
@@ -134,6 +144,72 @@ class SdfMlpPeGradFunction(torch.autograd.Function):
         g_sdf_bar = g_bar[:, 0:1].contiguous() if (need[1] and g_bar is not None) else None
         g_feat_bar = g_bar[:, 1:257].contiguous() if (need[2] and g_bar is not None) else None
         return (dx, g_sdf_bar, g_feat_bar, None, *([None] * 9), *dW, *db)
+
+
+def _sdf_backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, need_g, need_w, dq, inv_dq):
+    """The backward of SdfMlpPeGradFunction on the TMA-fed plane GEMMs (csrc/gemm3_tma.cu): every layer is ONE GEMM launch plus
+    ONE element-wise launch that also writes the next GEMM's operand planes."""
+    P, dev = x.shape[0], x.device
+    sc = [_INV_SQRT2 if l == 4 else 1.0 for l in range(9)]
+    # ---- upward: tangent pass ----
+    U = [torch.zeros((P, 64), dtype=torch.float32, device=dev)] + \
+        [torch.zeros((P, 512), dtype=torch.float32, device=dev) for _ in range(8)]
+    U[0][:, :39] = q * dq
+    U[4][:, 473:] = U[0][:, :39]
+    up = up0 = split_planes(U[0], P, 39, 64.0, ldp=64)
+    inj = [None] * 8
+    tz = None
+    for l in range(9):
+        o = outs[l]
+        tz = torch.empty((P, 512 if l < 8 else 264), dtype=torch.float32, device=dev)
+        mlp_layer_planes(up, ops.weight_planes(Ws[l]), P, o, ins[l], 4, tz, scale=sc[l])
+        if l < 8:
+            un = (torch.zeros((P, 512), dtype=torch.float16, device=dev), torch.zeros((P, 512), dtype=torch.float16, device=dev))
+            inj[l] = torch.zeros((P, 512), dtype=torch.float32, device=dev)
+            ops.softplus_tangent_planes(tz, act[l + 1], G[l], o, U[l + 1], un, inj[l])
+            if l == 3:      # layer 4 reads [tangent of a_4 (473) | tangent of PE (39)]
+                un[0][:, 473:] = up0[0][:, :39]
+                un[1][:, 473:] = up0[1][:, :39]
+            up = un
+    g_bar = tz[:, :257] * inv_dq if need_g else None
+    # ---- downward: backward-data pass that collects the local terms ----
+    dx = None
+    dW, db = [None] * 9, [None] * 9
+    if need_x or need_w:
+        dyn2 = grad_dyn_scale(*inj)
+        Zb = [None] * 8
+        Zb[7] = inj[7]
+        zp = split_planes(Zb[7], P, 512, 64.0, scale_dev=dyn2, ldp=512)
+        dpe4 = torch.zeros((P, 40), dtype=torch.float32, device=dev)
+        for l in range(7, 0, -1):
+            Zb[l - 1] = torch.zeros((P, 512), dtype=torch.float32, device=dev)
+            mlp_layer_planes(zp, ops.weight_planes(Ws[l], transpose=True), P, ins[l], outs[l], 1, Zb[l - 1],
+                             saved_input=act[l], scale=sc[l], dyn=dyn2, a_has_dyn=True, split=473 if l == 4 else 0,
+                             Y2=dpe4 if l == 4 else None)
+            zp = _plane_pair(P, 512, dev, zero=True)
+            ops.add_split_planes(Zb[l - 1], inj[l - 1], outs[l - 1], zp, 64.0, dyn2)
+        if need_x:
+            dpe0 = torch.zeros((P, 40), dtype=torch.float32, device=dev)
+            mlp_layer_planes(zp, ops.weight_planes(Ws[0], transpose=True), P, ins[0], outs[0], 0, dpe0,
+                             dyn=dyn2, a_has_dyn=True)
+            dx = pe_backward(x, dpe0, dpe4, ctx.pe_w, 6) * inv_dq
+        if need_w:
+            dW1, _ = mlp_bwd_weight(list(G), U, outs, ins, sc, dyn, want_bias=False)
+            dW2, db2 = mlp_bwd_weight(Zb, list(act[:8]), outs[:8], ins[:8], sc[:8], dyn2, want_bias=True)
+            for l in range(9):
+                dW[l] = (dW1[l] + dW2[l]) * inv_dq if l < 8 else dW1[l] * inv_dq
+                db[l] = db2[l] * inv_dq if l < 8 else None      # the input gradient does not depend on the last bias
+    g_sdf_bar = g_bar[:, 0:1].contiguous() if (need[1] and g_bar is not None) else None
+    g_feat_bar = g_bar[:, 1:257].contiguous() if (need[2] and g_bar is not None) else None
+    return (dx, g_sdf_bar, g_feat_bar, None, *([None] * 9), *dW, *db)
+
+
+SdfMlpPeGradFunction._backward_planes = staticmethod(_sdf_backward_planes)
+
+
+def _plane_pair(rows, cols, dev, zero=False):
+    mk = torch.zeros if zero else torch.empty
+    return (mk((rows, cols), dtype=torch.float16, device=dev), mk((rows, cols), dtype=torch.float16, device=dev))
 
 
 def sdf_input_grad(x, g_sdf, g_feat, pe_w, act, Ws, bs):

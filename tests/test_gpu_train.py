@@ -113,9 +113,9 @@ def test_loss_backward_matches_reference_autograd(tag):
         assert a < (2e-4 if n.endswith("sum") else 3e-5), table
 
 
-def test_create_graph_goes_through_the_torch_graph_and_matches():
-    """gradient(x) with create_graph=True (network.py:121-133; eikonal term) re-runs the network as a torch graph inside
-    the Function's backward: second-order gradients exist and agree with the all-torch module."""
+def test_create_graph_input_gradient_matches_the_all_torch_module():
+    """gradient(x) with create_graph=True (network.py:121-133; eikonal term): second-order gradients through the fused
+    reverse chain (recmv_b200/second_order.py) agree with the all-torch module (float64 parity: test_gpu_second_order.py)."""
     net = testing.build_sdf(getTmpSdf, seed=0, perturb_seed=101).to(DEV)
     x0 = (torch.rand((512, 3), generator=synth.generator(5)) * 1.2 - 0.6).to(DEV)
 
