@@ -264,6 +264,10 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
 
 // Passes 3 and 4, one warp per segment, same decode as the count pass.  `cap` = capacity (rows) of the output buffer:
 // a segment whose rows would not fit sets totals[2] and writes nothing (the host grows the buffer and re-runs).
+// Active cells are rare (1-2 %) and clustered: a lane whose 32-cell run lies along the surface would own most of the
+// warp's work.  So the warp first COMPACTS its active cells (cell order = lane-major, bit order) into a shared-memory
+// list, then walks the list 32 cells per round, one cell per lane: every lane does the same amount of work, and the row
+// offsets (segment base + exclusive prefix in cell order) are exactly those of a serial sweep.
 template <bool kFaces>
 __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
     const float* __restrict__ sdf, int NX, int NY, int NZ, float iso,
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
     int* __restrict__ cellinfo, float sx, float sy, float sz, float ox, float oy, float oz,
     float* __restrict__ verts, long long* __restrict__ faces, long long cap, int* __restrict__ totals, int nseg,
     FastDiv dplane, FastDiv dnz) {
+  __shared__ unsigned s_list[kMcWarpBlock / 32][kMcThreads];   // (cell within segment) | cube index << 10
   const unsigned N = (unsigned)NX * NY * NZ, plane = (unsigned)NY * NZ;
   const int lane = threadIdx.x & 31;
   const int seg = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
@@ -281,11 +286,12 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
   const int seg_begin = kFaces ? segoff.y : segoff.x;
   if (seg_end == seg_begin) return;   // nothing to emit here
   if ((long long)seg_end > cap) { if (lane == 0) totals[2] = 1; return; }
-  const unsigned b = (unsigned)seg * kMcThreads + 32u * lane;
+  const unsigned seg_base = (unsigned)seg * kMcThreads;
+  const unsigned b = seg_base + 32u * lane;
   RunMasks r;
   r.active = 0u;
   if (b < N) r = decode_run(bits, b, (unsigned)NZ, plane);
-  // first sweep over my active cells: how many rows do I emit
+  // sweep 1: drop the "cells" on the far faces of the grid, count mine
   int mine = 0;
   {
     unsigned a = r.active;
@@ -293,25 +299,38 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
       const int t = __ffs(a) - 1;
       a &= a - 1;
       int i, j, k;
-      if (!cell_coords(b + t, N, NX, NY, NZ, plane, dplane, dnz, i, j, k)) { r.active &= ~(1u << t); continue; }
-      const int ci = cube_index(r, t);
-      mine += kFaces ? (int)g_mc_ntri[ci] : (int)(g_mc_vinfo[ci] >> 6);
+      if (!cell_coords(b + t, N, NX, NY, NZ, plane, dplane, dnz, i, j, k)) r.active &= ~(1u << t);
+      else ++mine;
     }
   }
-  int row_total;
-  int off = seg_begin + warp_excl_scan(mine, lane, &row_total);
-  unsigned a = r.active;   // invalid "cells" were removed above
-  while (a) {
-    const int t = __ffs(a) - 1;
-    a &= a - 1;
-    const unsigned idx = b + t;
+  int n_cells;
+  int pos = warp_excl_scan(mine, lane, &n_cells);
+  // sweep 2: compact (cell, cube index) into the warp's list
+  unsigned* list = s_list[threadIdx.x >> 5];
+  {
+    unsigned a = r.active;
+    while (a) {
+      const int t = __ffs(a) - 1;
+      a &= a - 1;
+      list[pos++] = (unsigned)(32 * lane + t) | ((unsigned)cube_index(r, t) << 10);
+    }
+  }
+  __syncwarp();
+  int carry = seg_begin;
+  for (int base = 0; base < n_cells; base += 32) {
+    const bool have = base + lane < n_cells;
+    const unsigned rec = have ? list[base + lane] : 0u;
+    const int ci = (int)(rec >> 10);
+    const int info = kFaces ? 0 : (int)g_mc_vinfo[ci];
+    const int cnt = !have ? 0 : (kFaces ? (int)g_mc_ntri[ci] : (info >> 6));
+    int round_total;
+    const int off = carry + warp_excl_scan(cnt, lane, &round_total);
+    carry += round_total;
+    if (cnt == 0) continue;
+    const unsigned idx = seg_base + (rec & 1023u);
     int i, j, k;
     cell_coords(idx, N, NX, NY, NZ, plane, dplane, dnz, i, j, k);
-    const int ci = cube_index(r, t);
     if (!kFaces) {
-      const int info = g_mc_vinfo[ci];
-      const int cnt = info >> 6;
-      if (cnt == 0) continue;
       const int vbase = off;
       cellinfo[idx] = (vbase << 6) | (info & 63);
       const float* p = sdf + idx;
@@ -333,9 +352,7 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
         float* o = verts + (size_t)(vbase + r8) * 3;
         o[0] = fmaf(fX, sx, ox); o[1] = fmaf(fY, sy, oy); o[2] = fmaf(fZ + o_, sz, oz);
       }
-      off += cnt;
     } else {
-      const int cnt = g_mc_ntri[ci];
       const long long fbase = off;
       for (int tt = 0; tt < cnt; ++tt) {
 #pragma unroll
@@ -346,13 +363,12 @@ __global__ void __launch_bounds__(kMcWarpBlock) mc_emit_kernel(
           const int d = (int)(ow >> 24);
           long long vid = -1;
           if (oi < NX - 1 && oj < NY - 1 && ok < NZ - 1) {
-            const int info = cellinfo[((int64_t)oi * NY + oj) * NZ + ok];
-            vid = (long long)(info >> 6) + ((info >> (2 * d)) & 3);
+            const int oinfo = cellinfo[((int64_t)oi * NY + oj) * NZ + ok];
+            vid = (long long)(oinfo >> 6) + ((oinfo >> (2 * d)) & 3);
           }
           faces[(fbase + tt) * 3 + (2 - c)] = vid;  // reversed winding (CudaKernels.cu:502)
         }
       }
-      off += cnt;
     }
   }
 }
