@@ -113,26 +113,41 @@ class Seg3dLossless(nn.Module):
             return None
         return net, ratio, mode
 
+    def _host_consts(self):
+        """Host copies of the constant buffers the sweep's control flow needs (resolutions, box) and the coarse level's
+        lattice coordinates (the reference registers those as its `init_coords` buffer): read back once per buffer version,
+        not once per call -- the buffers live on the device, and every `int(v)` / `tolist()` on them is a blocking copy
+        (25 of them per extraction before this cache)."""
+        bufs = (self.resolutions, self.b_min, self.b_max)
+        key = tuple((b.data_ptr(), b._version, str(b.device)) for b in bufs)
+        hc = getattr(self, "_hc", None)
+        if hc is None or hc[0] != key:
+            res = [tuple(int(v) for v in r) for r in self.resolutions.cpu().tolist()]
+            b_min, b_max = self.b_min.view(-1).cpu().tolist(), self.b_max.view(-1).cpu().tolist()
+            dev = self.b_min.device
+            final = torch.tensor(res[-1])
+            coords = create_grid3D(0, final - 1, steps=torch.tensor(res[0]), device=dev).contiguous()
+            hc = (key, res, b_min, b_max, coords)
+            self._hc = hc
+        return hc[1:]
+
     def _forward_device(self, net, ratio, mode):
         """Same sweep, same voxels re-queried, same arithmetic for the query points -- as a device worklist: per level
         ONE host read (statistics / overflow / "were there conflicts left"), no nonzero / unique / index scatter.
         The grid equals the torch-op path's bit for bit (tests/test_gpu_surface.py)."""
         from .. import ops
         dev = self.b_min.device
-        final = self.resolutions[-1]
-        Wf, Hf, Df = (int(v) for v in final)
-        b_min, b_max = self.b_min.view(-1).tolist(), self.b_max.view(-1).tolist()
+        resolutions, b_min, b_max, coords0 = self._host_consts()
+        Wf, Hf, Df = resolutions[-1]
         packed, pe_w = net.packed_weights(), net._pe_weights(ratio)
         calculated = torch.zeros((Df, Hf, Wf), dtype=torch.uint8, device=dev)
         self.stats = []
         occ, done = None, None
-        for li, res in enumerate(self.resolutions):
-            W, H, D = (int(v) for v in res)
+        for li, (W, H, D) in enumerate(resolutions):
             stride = [(Wf - 1) // max(W - 1, 1), (Hf - 1) // max(H - 1, 1), (Df - 1) // max(D - 1, 1)]
             if li == 0:
-                coords = create_grid3D(0, final.to(dev) - 1, steps=res.to(dev), device=dev).contiguous()
                 with torch.no_grad():
-                    occ = self.batch_eval(coords.unsqueeze(0)).view(1, 1, D, H, W).float().contiguous()
+                    occ = self.batch_eval(coords0.unsqueeze(0)).view(1, 1, D, H, W).float().contiguous()
                 done = torch.ones((D, H, W), dtype=torch.uint8, device=dev)
                 calculated[::stride[2], ::stride[1], ::stride[0]] = 1
                 self.stats.append((W, H, D, D * H * W))
