@@ -255,6 +255,197 @@ gemm3_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient on the SAME planes:  dW[m][n] = sum_p G[p][m] X[p][n]  (m = output row, n = input column, p = sample).
+// Both operands are the row-major planes the layer GEMMs already wrote ([P][ld], the reduction index p is the ROW), i.e.
+// they are MN-major for this product.  tcgen05 reads MN-major operands natively (instruction-descriptor bits 15 / 16;
+// canonical SW128 layout ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in fp16 elements: a [8 k-rows][64 mn] swizzle atom of
+// 1024 B, atoms stacked along k every SBO = 1024 B and along mn every LBO), and that layout is exactly what TMA writes for
+// a {64 columns, 64 rows} SW128 box: a 128-wide operand tile is two such boxes 8192 B apart (LBO), one MMA (K = 16
+// samples) advances the start address by 16 rows = 2048 B.  So the weight gradient needs NO transposed copy of anything.
+// Work split: the output is at most 4 x 4 tiles, so the sample range is split over CTAs (grid = tiles x splits, one wave);
+// inside a CTA the accumulation runs in chunks of 32 K blocks alternating between two TMEM accumulators, and the epilogue
+// warps add each finished chunk into fp32 registers (a 10^5-sample reduction in one truncating accumulator would be cut
+// short, gemm3.cu); partial tiles go to a workspace and are summed in split order by a second launch (deterministic).
+struct WgParams {
+  float* ws;                 // [splits][tiles_m * 128][tiles_n * 128] raw partial sums (accumulator units, gain applied)
+  long long nkb;             // ceil(P / 64)
+  int M, N, tiles_m, tiles_n, splits, chunk_kb;
+  DevStatus* status;
+};
+
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const WgParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + kOffBar;
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(gbase + kOffMisc + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kOffMisc);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / prm.splits, split = blockIdx.x - tile * prm.splits;
+  const int tm = tile / prm.tiles_n, tn = tile - tm * prm.tiles_n;
+  const long long kb0 = prm.nkb * split / prm.splits, kb1 = prm.nkb * (split + 1) / prm.splits;
+  const long long nchunks = (kb1 - kb0 + prm.chunk_kb - 1) / prm.chunk_kb;
+
+  if (threadIdx.x == 0) {
+    *abort_flag = 0;
+    for (int s = 0; s < kStages; ++s) { mbar_init(BAR(kBarFull + s), 1); mbar_init(BAR(kBarEmpty + s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR(kBarAccFull + b), 1); mbar_init(BAR(kBarAccEmpty + b), kEpiWarps); }
+    fence_mbar_init();
+    prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      long long kbg = 0;
+      for (long long kb = kb0; kb < kb1; ++kb, ++kbg) {
+        const int s = (int)(kbg % kStages);
+        mbar_wait(BAR(kBarEmpty + s), (uint32_t)(((kbg / kStages) & 1) ^ 1), abort_flag, prm.status, 3800 + s);
+        const uint32_t st = base + (uint32_t)s * kStageBytes;
+        mbar_expect_tx_local(BAR(kBarFull + s), kStageBytes);
+        const int row = (int)(kb * kBK);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {   // the two 64-wide halves of each 128-wide operand tile
+          tma_load_2d(st + h * 8192u, &tm_a_hi, BAR(kBarFull + s), tm * kBM + 64 * h, row);
+          tma_load_2d(st + kPlane + h * 8192u, &tm_a_lo, BAR(kBarFull + s), tm * kBM + 64 * h, row);
+          tma_load_2d(st + 2 * kPlane + h * 8192u, &tm_b_hi, BAR(kBarFull + s), tn * kBN + 64 * h, row);
+          tma_load_2d(st + 3 * kPlane + h * 8192u, &tm_b_lo, BAR(kBarFull + s), tn * kBN + 64 * h, row);
+        }
+      }
+      for (long long k2 = kbg; k2 < kbg + kStages; ++k2) {
+        if (k2 - kStages < 0) continue;
+        const int s = (int)(k2 % kStages);
+        mbar_wait(BAR(kBarEmpty + s), (uint32_t)(((k2 / kStages) & 1) ^ 1), abort_flag, prm.status, 3850 + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_f16(kBM, kBN) | (1u << 15) | (1u << 16);   // A and B MN-major
+      long long kbg = 0;
+      for (long long ch = 0; ch < nchunks; ++ch) {
+        const int buf = (int)(ch & 1);
+        mbar_wait(BAR(kBarAccEmpty + buf), (uint32_t)(((ch >> 1) & 1) ^ 1), abort_flag, prm.status, 3900 + buf);
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + (uint32_t)(buf * kBN);
+        const long long c0 = kb0 + ch * prm.chunk_kb, c1 = c0 + prm.chunk_kb < kb1 ? c0 + prm.chunk_kb : kb1;
+        for (long long kb = c0; kb < c1; ++kb, ++kbg) {
+          const int s = (int)(kbg % kStages);
+          mbar_wait(BAR(kBarFull + s), (uint32_t)((kbg / kStages) & 1), abort_flag, prm.status, 3950 + s);
+          tc_fence_after();
+          const uint32_t st = base + (uint32_t)s * kStageBytes;
+          const uint64_t a_hi = smem_desc_sw128_mn(st), a_lo = smem_desc_sw128_mn(st + kPlane);
+          const uint64_t b_hi = smem_desc_sw128_mn(st + 2 * kPlane), b_lo = smem_desc_sw128_mn(st + 3 * kPlane);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_1cta(dcol, a_lo + 128 * k, b_hi + 128 * k, idesc, (kb == c0 && k == 0) ? 0u : 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_1cta(dcol, a_hi + 128 * k, b_lo + 128 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_1cta(dcol, a_hi + 128 * k, b_hi + 128 * k, idesc, 1u);
+          umma_commit_1cta(BAR(kBarEmpty + s));
+        }
+        umma_commit_1cta(BAR(kBarAccFull + buf));
+      }
+    }
+  } else {
+    const int q = warp & 3, cg = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (long long ch = 0; ch < nchunks; ++ch) {
+      const int buf = (int)(ch & 1);
+      const long long c0 = kb0 + ch * prm.chunk_kb;
+      const int len = (int)((c0 + prm.chunk_kb < kb1 ? c0 + prm.chunk_kb : kb1) - c0);
+      const float gain = acc_trunc_gain(len);
+      mbar_wait(BAR(kBarAccFull + buf), (uint32_t)((ch >> 1) & 1), abort_flag, prm.status, 3980 + buf);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kBN + cg * 32), r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(r[j]), gain, acc[j]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_local(BAR(kBarAccEmpty + buf));
+    }
+    const long long ldw = (long long)prm.tiles_n * kBN;
+    float* d = prm.ws + ((long long)split * prm.tiles_m * kBM + tm * kBM + row) * ldw + tn * kBN + cg * 32;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4)
+      *reinterpret_cast<float4*>(d + 4 * j4) = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+namespace {
+
+// dW[m][n] = unscale * sum over splits (in split order) of the partial tiles
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride,
+                                                           long long ldw, int M, int N, float scale,
+                                                           const float* __restrict__ dyn_scale, float* __restrict__ dW,
+                                                           long long ldd) {
+  const float s = scale / (dyn_scale ? __ldg(dyn_scale) : 1.f);
+  const long long total = (long long)M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+    float a = 0.f;
+    for (int k = 0; k < splits; ++k) a += ws[k * split_stride + m * ldw + n];
+    dW[m * ldd + n] = a * s;
+  }
+}
+
+// column sums of an fp32 matrix (bias gradient), two deterministic stages: partial[rs][c] over row slab rs, then the slabs
+constexpr int kCsSlabs = 128;
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ g, long long ld, long long R, int C,
+                                                             float* __restrict__ partial) {
+  __shared__ float sh[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+  const long long r0 = R * blockIdx.y / kCsSlabs, r1 = R * (blockIdx.y + 1) / kCsSlabs;
+  float a = 0.f;
+  if (c < C)
+    for (long long r = r0 + ry; r < r1; r += 8) a += __ldg(g + r * ld + c);
+  sh[ry][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][threadIdx.x & 31];
+    partial[(long long)blockIdx.y * C + c] = t;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int k = 0; k < kCsSlabs; ++k) t += partial[(long long)k * C + c];
+  out[c] = t;
+}
+
+}  // namespace
+
 namespace {
 
 // fp32 [R][C] (row stride ld) -> fp16 hi / lo planes of scale * value: out[r][c] (transpose == 0, row stride ldp) or
@@ -343,7 +534,8 @@ __global__ void __launch_bounds__(256) pe_forward_planes_kernel(const float* __r
   }
 }
 
-int make_plane_tmap(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_elems) {
+int make_plane_tmap(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_pitch_elems,
+                    uint32_t box_rows = 128) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     cudaDriverEntryPointQueryResult q;
@@ -355,7 +547,7 @@ int make_plane_tmap(CUtensorMap* out, const void* base, uint64_t cols, uint64_t 
   if (((uintptr_t)base & 15) != 0 || (row_pitch_elems & 7) != 0) return RECMV_E_SHAPE;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {row_pitch_elems * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -481,5 +673,73 @@ extern "C" int recmv_mlp_layer_planes(const void* a_hi, const void* a_lo, int64_
   const int total = prm.tiles_m * prm.tiles_n;
   const int grid = total < num_sms() ? total : num_sms();
   gemm3_tma_kernel<<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(ta_h, ta_l, tb_h, tb_l, prm);
+  return launch_status();
+}
+
+// dW [out_dim][in_dim] (row stride in_dim) = scale * G^T X from the planes the layer GEMMs wrote: g planes [P][ldg_p] hold
+// 64 * dyn * g (columns < out_dim), x planes [P][ldx_p] hold 64 * x (columns < in_dim).  workspace: fp32, at least
+// recmv_mlp_wgrad_workspace_floats() elements, reused across calls on one stream.
+extern "C" size_t recmv_mlp_wgrad_workspace_floats(void) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (size_t)(num_sms() + 16) * kBM * kBN;
+}
+
+extern "C" int recmv_mlp_wgrad_planes(const void* g_hi, const void* g_lo, int64_t ldg_p, const void* x_hi, const void* x_lo,
+                                      int64_t ldx_p, int64_t P, int out_dim, int in_dim, float scale, const float* dyn_scale,
+                                      float* workspace, float* dW, recmv_stream_t stream) {
+  if (P < 0 || out_dim <= 0 || in_dim <= 0) return RECMV_E_SHAPE;
+  if (!g_hi || !g_lo || !x_hi || !x_lo || !workspace || !dW) return RECMV_E_NULL;
+  if (P > (int64_t)1 << 30) return RECMV_E_RANGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (P == 0) return (int)cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)out_dim * in_dim, st);
+  CUtensorMap ta_h, ta_l, tb_h, tb_l;
+  int s = make_plane_tmap(&ta_h, g_hi, (uint64_t)out_dim, (uint64_t)P, (uint64_t)ldg_p, 64);
+  if (!s) s = make_plane_tmap(&ta_l, g_lo, (uint64_t)out_dim, (uint64_t)P, (uint64_t)ldg_p, 64);
+  if (!s) s = make_plane_tmap(&tb_h, x_hi, (uint64_t)in_dim, (uint64_t)P, (uint64_t)ldx_p, 64);
+  if (!s) s = make_plane_tmap(&tb_l, x_lo, (uint64_t)in_dim, (uint64_t)P, (uint64_t)ldx_p, 64);
+  if (s) return s;
+  void* sd = nullptr;
+  s = device_status_record(&sd);
+  if (s) return s;
+  static bool attr_done[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 15]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_done[dev & 15] = true;
+  }
+  WgParams prm = {};
+  prm.ws = workspace;
+  prm.nkb = (P + kBK - 1) / kBK;
+  prm.M = out_dim; prm.N = in_dim;
+  prm.tiles_m = (out_dim + kBM - 1) / kBM; prm.tiles_n = (in_dim + kBN - 1) / kBN;
+  const int tiles = prm.tiles_m * prm.tiles_n;
+  int splits = num_sms() / tiles;
+  if (splits < 1) splits = 1;
+  if ((long long)splits > prm.nkb) splits = (int)prm.nkb;
+  prm.splits = splits;
+  prm.chunk_kb = 32;
+  prm.status = (DevStatus*)sd;
+  gemm3_wgrad_kernel<<<tiles * splits, kThreads, kSmemBytes, st>>>(ta_h, ta_l, tb_h, tb_l, prm);
+  s = launch_status();
+  if (s) return s;
+  const long long ldw = (long long)prm.tiles_n * kBN, split_stride = (long long)prm.tiles_m * kBM * ldw;
+  wgrad_reduce_kernel<<<stride_grid((int64_t)out_dim * in_dim, 256, 4), 256, 0, st>>>(
+      workspace, splits, split_stride, ldw, out_dim, in_dim, scale / (64.f * 64.f), dyn_scale, dW, in_dim);
+  return launch_status();
+}
+
+// out[c] = sum_r g[r][c], c < cols (bias gradient); partial: fp32 scratch of 128 * cols elements
+extern "C" int recmv_colsum(const float* g, int64_t ld, int64_t rows, int cols, float* partial, float* out,
+                            recmv_stream_t stream) {
+  if (rows < 0 || cols <= 0) return RECMV_E_SHAPE;
+  if (!g || !partial || !out) return RECMV_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  colsum_partial_kernel<<<dim3((unsigned)((cols + 31) / 32), kCsSlabs), 256, 0, st>>>(g, ld, rows, cols, partial);
+  int s = launch_status();
+  if (s) return s;
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, st>>>(partial, cols, out);
   return launch_status();
 }

@@ -614,6 +614,42 @@ def mlp_layer_planes(a_planes, b_planes, M, N, K, mode, Y, bias=None, saved_inpu
     return Y
 
 
+_WGRAD_WS = {}
+
+
+def _wgrad_workspace(dev):
+    key = (dev.type, dev.index)
+    if key not in _WGRAD_WS:
+        with torch.cuda.device(dev):
+            n = int(_lib.load().recmv_mlp_wgrad_workspace_floats())
+        _WGRAD_WS[key] = (torch.empty((n,), dtype=torch.float32, device=dev), torch.empty((128 * 512,), dtype=torch.float32, device=dev))
+    return _WGRAD_WS[key]
+
+
+def mlp_wgrad_planes(g_planes, x_planes, P, out_dim, in_dim, scale=1.0, dyn=None):
+    """dW [out_dim, in_dim] = scale * G^T X from the operand planes the layer GEMMs wrote (recmv_mlp_wgrad_planes)."""
+    gh, gl = g_planes
+    xh, xl = x_planes
+    dev = gh.device
+    ws, _ = _wgrad_workspace(dev)
+    dW = torch.empty((out_dim, in_dim), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().recmv_mlp_wgrad_planes(_ptr(gh), _ptr(gl), gh.stride(0), _ptr(xh), _ptr(xl), xh.stride(0), int(P),
+                                                 int(out_dim), int(in_dim), float(scale), _ptr(dyn), _ptr(ws), _ptr(dW),
+                                                 _stream(gh)), "recmv_mlp_wgrad_planes")
+    return dW
+
+
+def colsum(G, cols):
+    """sum over rows of G[:, :cols] (fp32, deterministic two-stage reduction): the bias gradient."""
+    _, part = _wgrad_workspace(G.device)
+    out = torch.empty((cols,), dtype=torch.float32, device=G.device)
+    with torch.cuda.device(G.device):
+        check(_lib.load().recmv_colsum(_ptr(G), G.stride(0), G.shape[0], int(cols), _ptr(part), _ptr(out), _stream(G)),
+              "recmv_colsum")
+    return out
+
+
 def softplus_tangent_planes(tz, a, h, cols, u, u_planes, inj, plane_scale=64.0):
     """u[:, :cols] = softplus_100'(z) * tz (+ planes), inj[:, :cols] = softplus_100''(z) * (h / softplus') * tz, from the saved
     softplus output a (second_order.py's tangent pass; one launch)."""
@@ -720,7 +756,11 @@ class SdfMlpTrainFunction(torch.autograd.Function):
                               pre_scale=_INV_SQRT2 if l == 4 else 1.0)
             mlp_fwd_layer(act[8], Ws[8], bs[8], 257, 512, ACT_NONE, sdf, split=1, Y2=feat)
         ctx.pe_w, ctx.mode = [float(w) for w in pe_w], mode
-        ctx.save_for_backward(x, *Wb, *act)
+        ctx.has_planes = TRAIN_GEMM == "planes"
+        if ctx.has_planes:      # the layer inputs' operand planes feed the weight gradient too (recmv_mlp_wgrad_planes)
+            ctx.save_for_backward(x, *Wb, *act, *[t for pair in xp for t in pair])
+        else:
+            ctx.save_for_backward(x, *Wb, *act)
         return sdf, feat
 
     @staticmethod
@@ -765,8 +805,11 @@ class SdfMlpTrainFunction(torch.autograd.Function):
         outs = [w.shape[0] for w in Ws]
         ins = [w.shape[1] for w in Ws]
         dx = None
-        if TRAIN_GEMM == "planes":
+        planes = TRAIN_GEMM == "planes" and ctx.has_planes
+        GP = [None] * 9
+        if planes:
             gp = split_planes(G8, P, 257, 64.0, scale_dev=dyn, ldp=264)       # cotangent planes carry 64 * dyn
+            GP[8] = gp
             for l in range(8, 0, -1):
                 G[l - 1] = torch.empty((P, 512), dtype=torch.float32, device=dev)
                 gprev = (torch.empty((P, 512), dtype=torch.float16, device=dev), torch.empty((P, 512), dtype=torch.float16, device=dev))
@@ -775,6 +818,7 @@ class SdfMlpTrainFunction(torch.autograd.Function):
                                  dyn=dyn, a_has_dyn=True, split=473 if l == 4 else 0, Y2=dpe4 if l == 4 else None,
                                  y_planes=gprev, planes_with_dyn=True)
                 gp = gprev
+                GP[l - 1] = gp
             if need_x:
                 dpe0 = torch.empty((P, 40), dtype=torch.float32, device=dev)
                 mlp_layer_planes(gp, weight_planes(Ws[0], transpose=True), P, ins[0], outs[0], 0, dpe0, dyn=dyn, a_has_dyn=True)
@@ -782,7 +826,7 @@ class SdfMlpTrainFunction(torch.autograd.Function):
         else:
             for l in range(8, 0, -1):
                 G[l - 1] = torch.empty((P, 512), dtype=torch.float32, device=dev)
-                mlp_bwd_data_layer(G[l], Ws[l], outs[l], ins[l], act[l], ACT_SOFTPLUS100, G[l - 1],
+                mlp_bwd_data_layer(G[l], Ws[l].detach(), outs[l], ins[l], act[l], ACT_SOFTPLUS100, G[l - 1],
                                    split=473 if l == 4 else 0, D2=dpe4 if l == 4 else None,
                                    out_scale=_INV_SQRT2 if l == 4 else 1.0, dyn_scale=dyn)
             if need_x:
@@ -790,7 +834,13 @@ class SdfMlpTrainFunction(torch.autograd.Function):
                 mlp_bwd_data_layer(G[0], Ws[0], outs[0], ins[0], None, ACT_NONE, dpe0, dyn_scale=dyn)
                 dx = pe_backward(x, dpe0, dpe4, ctx.pe_w, 6)
         dW, db = [None] * 9, [None] * 9
-        if need_w:
+        if need_w and planes:
+            # weight gradient straight from the planes both passes wrote (MN-major operands, no transposed copies)
+            xpl = saved[28:46]
+            for l in range(9):
+                dW[l] = mlp_wgrad_planes(GP[l], (xpl[2 * l], xpl[2 * l + 1]), P, outs[l], ins[l], _INV_SQRT2 if l == 4 else 1.0, dyn)
+                db[l] = colsum(G[l], outs[l])
+        elif need_w:
             dW, db = mlp_bwd_weight(G, list(act), outs, ins, [_INV_SQRT2 if l == 4 else 1.0 for l in range(9)], dyn)
         return (dx, None, None, None, *dW, *db)
 

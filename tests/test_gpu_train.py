@@ -243,3 +243,21 @@ def test_rendernet_backward_matches_reference_autograd():
     print(table)
     for n, a, b in rows:
         assert a < (2e-4 if n.endswith("sum") else 3e-5), table
+
+
+@pytest.mark.parametrize("P,out_dim,in_dim", [(64, 128, 128), (3000, 473, 512), (1, 257, 512), (4097, 512, 39), (70000, 512, 512)])
+def test_wgrad_on_planes_matches_fp64(P, out_dim, in_dim):
+    """recmv_mlp_wgrad_planes (MN-major operands straight from the row-major planes) and recmv_colsum vs float64."""
+    g = synth.generator(40 + P % 7)
+    G = (torch.randn((P, 512), generator=g) * torch.exp(torch.randn((P, 1), generator=g)) * 1e-3).to(DEV)
+    X = torch.randn((P, 512), generator=g).abs().mul(0.3).to(DEV)
+    dyn = ops.grad_dyn_scale(G)
+    gp = ops.split_planes(G, P, out_dim, 64.0, scale_dev=dyn, ldp=512)
+    xp = ops.split_planes(X, P, in_dim, 64.0, ldp=512)
+    dW = ops.mlp_wgrad_planes(gp, xp, P, out_dim, in_dim, 0.5, dyn)
+    ref = 0.5 * G[:, :out_dim].double().T @ X[:, :in_dim].double()
+    e = merr(dW, ref)
+    db = ops.colsum(G, out_dim)
+    eb = merr(db, G[:, :out_dim].double().sum(0))
+    print(f"wgrad planes P={P} {out_dim}x{in_dim}: {e:.2e}  colsum {eb:.2e}")
+    assert e < (6e-6 if P > 10000 else 3e-6) and eb < 2e-6      # measured 3.3e-6 at 70 000 samples
