@@ -776,7 +776,8 @@ class SdfMlpTrainFunction(torch.autograd.Function):
             # chain as a differentiable op whose own backward is tangent + backward GEMMs on tcgen05 (second_order.py)
             from . import second_order
             SdfMlpTrainFunction.last_backward = "fused-tcgen05 (create_graph, input gradient)"
-            dx = second_order.sdf_input_grad(x, g_sdf, g_feat, ctx.pe_w, act, Ws, bs) if need_x else None
+            dx = second_order.sdf_input_grad(x, g_sdf, g_feat, ctx.pe_w, act, Ws, bs,
+                                             saved[28:46] if ctx.has_planes else ()) if need_x else None
             return (dx, None, None, None, *([None] * 18))
         if torch.is_grad_enabled():
             # create_graph=True with parameter gradients in the graph: differentiate a torch graph of the same network
@@ -854,6 +855,7 @@ def _plain_mlp_forward(X0, Ws, bs):
     n = len(Ws)
     planes = TRAIN_GEMM == "planes"
     xp = split_planes(X0, P, Ws[0].shape[1], 64.0, ldp=_pad8(X0.shape[1])) if planes else None
+    xplanes = []
     for l in range(n):
         o, i = Ws[l].shape
         last = l == n - 1
@@ -862,15 +864,17 @@ def _plain_mlp_forward(X0, Ws, bs):
             yp = None if last else (torch.empty((P, _pad8(o)), dtype=torch.float16, device=dev),
                                     torch.empty((P, _pad8(o)), dtype=torch.float16, device=dev))
             mlp_layer_planes(xp, split_planes(Ws[l], o, i, 1024.0), P, o, i, 4 if last else 6, Y, bias=bs[l], y_planes=yp)
+            xplanes += [xp[0], xp[1]]
             xp = yp
         else:
             mlp_fwd_layer(acts[l], Ws[l], bs[l], o, i, ACT_NONE if last else ACT_RELU, Y)
         acts.append(Y)
-    return acts[-1][:, :Ws[-1].shape[0]], acts[:-1]
+    return acts[-1][:, :Ws[-1].shape[0]], acts[:-1], xplanes
 
 
-def _plain_mlp_backward(g_out, Ws, acts, need_w, need_x0):
-    """g_out [P, out_last] -> (dX0 [P, in_0 padded] or None, dW list, db list) for the ReLU MLP."""
+def _plain_mlp_backward(g_out, Ws, acts, need_w, need_x0, xplanes=()):
+    """g_out [P, out_last] -> (dX0 [P, in_0 padded] or None, dW list, db list) for the ReLU MLP.  xplanes: the layer inputs'
+    operand planes from the forward (flat hi, lo list) -- with them the weight gradient runs on the planes as well."""
     P, dev = g_out.shape[0], g_out.device
     n = len(Ws)
     o_last = Ws[-1].shape[0]
@@ -880,6 +884,8 @@ def _plain_mlp_backward(g_out, Ws, acts, need_w, need_x0):
     dyn = grad_dyn_scale(G[n - 1])
     planes = TRAIN_GEMM == "planes"
     gp = split_planes(G[n - 1], P, o_last, 64.0, scale_dev=dyn, ldp=_pad8(o_last)) if planes else None
+    GP = [None] * n
+    GP[n - 1] = gp
     for l in range(n - 1, 0, -1):
         o, i = Ws[l].shape
         G[l - 1] = torch.empty((P, i), dtype=torch.float32, device=dev)
@@ -888,6 +894,7 @@ def _plain_mlp_backward(g_out, Ws, acts, need_w, need_x0):
             mlp_layer_planes(gp, split_planes(Ws[l].detach(), o, i, 1024.0, transpose=True), P, i, o, 2, G[l - 1],
                              saved_input=acts[l], dyn=dyn, a_has_dyn=True, y_planes=gprev, planes_with_dyn=True)
             gp = gprev
+            GP[l - 1] = gp
         else:
             mlp_bwd_data_layer(G[l], Ws[l], o, i, acts[l], ACT_RELU, G[l - 1], dyn_scale=dyn)
     dX0 = None
@@ -900,7 +907,12 @@ def _plain_mlp_backward(g_out, Ws, acts, need_w, need_x0):
         else:
             mlp_bwd_data_layer(G[0], Ws[0], o, i, None, ACT_NONE, dX0, dyn_scale=dyn)
     dW, db = [None] * n, [None] * n
-    if need_w:
+    if need_w and planes and len(xplanes) == 2 * n:
+        for l in range(n):
+            o, i = Ws[l].shape
+            dW[l] = mlp_wgrad_planes(GP[l], (xplanes[2 * l], xplanes[2 * l + 1]), P, o, i, 1.0, dyn)
+            db[l] = colsum(G[l], o)
+    elif need_w:
         dW, db = mlp_bwd_weight(G, list(acts), [w.shape[0] for w in Ws], [w.shape[1] for w in Ws], None, dyn)
     return dX0, dW, db
 
@@ -928,9 +940,9 @@ class TranslatorTrainFunction(torch.autograd.Function):
         X0 = torch.zeros((P, 168), dtype=torch.float32, device=dev)
         pe_forward(ps, pe_w, 6, X0)
         X0[:, 39:167] = conds.detach()[batch_inds]
-        out, acts = _plain_mlp_forward(X0, Ws, bs)
+        out, acts, xplanes = _plain_mlp_forward(X0, Ws, bs)
         ctx.pe_w, ctx.n = [float(w) for w in pe_w], n
-        ctx.save_for_backward(ps, conds, batch_inds, *Wb, *acts)
+        ctx.save_for_backward(ps, conds, batch_inds, *Wb, *acts, *xplanes)
         return out.contiguous()
 
     @staticmethod
@@ -938,7 +950,7 @@ class TranslatorTrainFunction(torch.autograd.Function):
         n = ctx.n
         saved = ctx.saved_tensors
         ps, conds, batch_inds = saved[:3]
-        Ws, bs, acts = saved[3:3 + n], saved[3 + n:3 + 2 * n], saved[3 + 2 * n:]
+        Ws, bs, acts, xplanes = saved[3:3 + n], saved[3 + n:3 + 2 * n], saved[3 + 2 * n:3 + 3 * n], saved[3 + 3 * n:]
         need = ctx.needs_input_grad
         if torch.is_grad_enabled() and _inputs_only(any(need[4:])):
             # utils.compute_Jacobian(..., create_graph=True) of the deformation regulariser: see second_order.py
@@ -958,7 +970,7 @@ class TranslatorTrainFunction(torch.autograd.Function):
             res = [next(gr) if t.requires_grad else None for t in [ps, conds] + list(Ws) + list(bs)]
             return (res[0], res[1], None, None, *res[2:])
         TranslatorTrainFunction.last_backward = "fused-tcgen05"
-        dX0, dW, db = _plain_mlp_backward(g_off.contiguous().float(), Ws, acts, any(need[4:]), need[0] or need[1])
+        dX0, dW, db = _plain_mlp_backward(g_off.contiguous().float(), Ws, acts, any(need[4:]), need[0] or need[1], xplanes)
         dps = dconds = None
         if need[0]:
             dps = pe_backward(ps, dX0, None, ctx.pe_w, 6)
@@ -982,9 +994,9 @@ class RenderNetTrainFunction(torch.autograd.Function):
         pe_forward(view_dirs.detach().contiguous(), pe_w, 4, X0[:, 3:])
         X0[:, 30:33] = normals.detach()
         X0[:, 33:289] = feats.detach()
-        out, acts = _plain_mlp_forward(X0, Ws, bs)
+        out, acts, xplanes = _plain_mlp_forward(X0, Ws, bs)
         ctx.pe_w, ctx.n = [float(w) for w in pe_w], n
-        ctx.save_for_backward(points, normals, view_dirs, feats, *Wb, *acts)
+        ctx.save_for_backward(points, normals, view_dirs, feats, *Wb, *acts, *xplanes)
         return out.contiguous()
 
     @staticmethod
@@ -992,7 +1004,7 @@ class RenderNetTrainFunction(torch.autograd.Function):
         n = ctx.n
         saved = ctx.saved_tensors
         points, normals, view_dirs, feats = saved[:4]
-        Ws, bs, acts = saved[4:4 + n], saved[4 + n:4 + 2 * n], saved[4 + 2 * n:]
+        Ws, bs, acts, xplanes = saved[4:4 + n], saved[4 + n:4 + 2 * n], saved[4 + 2 * n:4 + 3 * n], saved[4 + 3 * n:]
         need = ctx.needs_input_grad
         if torch.is_grad_enabled() and _inputs_only(any(need[5:])):
             from . import second_order
@@ -1014,7 +1026,7 @@ class RenderNetTrainFunction(torch.autograd.Function):
             res = [next(gr) if t.requires_grad else None for t in allin]
             return (*res[:4], None, *res[4:])
         RenderNetTrainFunction.last_backward = "fused-tcgen05"
-        dX0, dW, db = _plain_mlp_backward(g_out.contiguous().float(), Ws, acts, any(need[5:]), any(need[:4]))
+        dX0, dW, db = _plain_mlp_backward(g_out.contiguous().float(), Ws, acts, any(need[5:]), any(need[:4]), xplanes)
         dp = dn = dv = df = None
         if need[0]:
             dp = dX0[:, 0:3].contiguous()

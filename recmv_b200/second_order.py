@@ -45,7 +45,7 @@ class SdfMlpPeGradFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, g_sdf, g_feat, pe_w, *rest):
-        act, Ws, bs = rest[:9], rest[9:18], rest[18:27]
+        act, Ws, bs, xplanes = rest[:9], rest[9:18], rest[18:27], rest[27:]
         P, dev = x.shape[0], x.device
         Wd = [w.detach().contiguous().float() for w in Ws]
         outs = [w.shape[0] for w in Wd]
@@ -62,9 +62,12 @@ class SdfMlpPeGradFunction(torch.autograd.Function):
         dpe0 = torch.zeros((P, 40), dtype=torch.float32, device=dev)
         if ops.TRAIN_GEMM == "planes":
             gp = split_planes(G8, P, 257, 64.0, scale_dev=dyn, ldp=264)
+            GP = [None] * 9
+            GP[8] = gp
             for l in range(8, 0, -1):
                 G[l - 1] = torch.zeros((P, 512), dtype=torch.float32, device=dev)
                 gprev = _plane_pair(P, 512, dev)
+                GP[l - 1] = gprev
                 mlp_layer_planes(gp, ops.weight_planes(Ws[l], transpose=True), P, ins[l], outs[l], 1, G[l - 1],
                                  saved_input=act[l], scale=_INV_SQRT2 if l == 4 else 1.0, dyn=dyn, a_has_dyn=True,
                                  split=473 if l == 4 else 0, Y2=dpe4 if l == 4 else None, y_planes=gprev, planes_with_dyn=True)
@@ -79,7 +82,9 @@ class SdfMlpPeGradFunction(torch.autograd.Function):
             mlp_bwd_data_layer(G[0], Wd[0], outs[0], ins[0], None, ACT_NONE, dpe0, dyn_scale=dyn)
         ctx.pe_w = [float(w) for w in pe_w]
         ctx.dims = (outs, ins)
-        ctx.save_for_backward(x, dyn, *act, *Ws, *G)
+        ctx.wgrad_planes = ops.TRAIN_GEMM == "planes" and len(xplanes) == 18
+        extra = ([t for pair in GP for t in pair] + list(xplanes)) if ctx.wgrad_planes else []
+        ctx.save_for_backward(x, dyn, *act, *Ws, *G, *extra)
         return (dpe0 + dpe4)[:, :39].contiguous()
 
     @staticmethod
@@ -97,7 +102,9 @@ class SdfMlpPeGradFunction(torch.autograd.Function):
         dq = grad_dyn_scale(q)
         inv_dq = 1.0 / dq
         if ops.TRAIN_GEMM == "planes":
-            return SdfMlpPeGradFunction._backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, need_g, need_w, dq, inv_dq)
+            res = SdfMlpPeGradFunction._backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, need_g, need_w, dq,
+                                                        inv_dq, saved[29:])
+            return (*res, *([None] * (len(need) - len(res))))
         # ---- upward: tangent pass with tangent of PE = q (scaled into [1,2) by dq; everything below is linear in it) ----
         U = [torch.zeros((P, 64), dtype=torch.float32, device=dev)] + \
             [torch.zeros((P, 512), dtype=torch.float32, device=dev) for _ in range(8)]
@@ -143,10 +150,10 @@ class SdfMlpPeGradFunction(torch.autograd.Function):
                     db[l] = db2[l] * inv_dq if l < 8 else None      # the input gradient does not depend on the last bias
         g_sdf_bar = g_bar[:, 0:1].contiguous() if (need[1] and g_bar is not None) else None
         g_feat_bar = g_bar[:, 1:257].contiguous() if (need[2] and g_bar is not None) else None
-        return (dx, g_sdf_bar, g_feat_bar, None, *([None] * 9), *dW, *db)
+        return (dx, g_sdf_bar, g_feat_bar, None, *([None] * 9), *dW, *db, *([None] * (len(need) - 31)))
 
 
-def _sdf_backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, need_g, need_w, dq, inv_dq):
+def _sdf_backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, need_g, need_w, dq, inv_dq, extra=()):
     """The backward of SdfMlpPeGradFunction on the TMA-fed plane GEMMs (csrc/gemm3_tma.cu): every layer is ONE GEMM launch plus
     ONE element-wise launch that also writes the next GEMM's operand planes."""
     P, dev = x.shape[0], x.device
@@ -157,6 +164,7 @@ def _sdf_backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, ne
     U[0][:, :39] = q * dq
     U[4][:, 473:] = U[0][:, :39]
     up = up0 = split_planes(U[0], P, 39, 64.0, ldp=64)
+    UP = [up0] + [None] * 8
     inj = [None] * 8
     tz = None
     for l in range(9):
@@ -171,6 +179,7 @@ def _sdf_backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, ne
                 un[0][:, 473:] = up0[0][:, :39]
                 un[1][:, 473:] = up0[1][:, :39]
             up = un
+            UP[l + 1] = un
     g_bar = tz[:, :257] * inv_dq if need_g else None
     # ---- downward: backward-data pass that collects the local terms ----
     dx = None
@@ -180,6 +189,8 @@ def _sdf_backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, ne
         Zb = [None] * 8
         Zb[7] = inj[7]
         zp = split_planes(Zb[7], P, 512, 64.0, scale_dev=dyn2, ldp=512)
+        ZP = [None] * 8
+        ZP[7] = zp
         dpe4 = torch.zeros((P, 40), dtype=torch.float32, device=dev)
         for l in range(7, 0, -1):
             Zb[l - 1] = torch.zeros((P, 512), dtype=torch.float32, device=dev)
@@ -188,12 +199,22 @@ def _sdf_backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, ne
                              Y2=dpe4 if l == 4 else None)
             zp = _plane_pair(P, 512, dev, zero=True)
             ops.add_split_planes(Zb[l - 1], inj[l - 1], outs[l - 1], zp, 64.0, dyn2)
+            ZP[l - 1] = zp
         if need_x:
             dpe0 = torch.zeros((P, 40), dtype=torch.float32, device=dev)
             mlp_layer_planes(zp, ops.weight_planes(Ws[0], transpose=True), P, ins[0], outs[0], 0, dpe0,
                              dyn=dyn2, a_has_dyn=True)
             dx = pe_backward(x, dpe0, dpe4, ctx.pe_w, 6) * inv_dq
-        if need_w:
+        if need_w and getattr(ctx, "wgrad_planes", False):
+            # both outer products straight from the planes the passes wrote (recmv_mlp_wgrad_planes)
+            GPl, XPl = extra[:18], extra[18:36]
+            for l in range(9):
+                w1 = ops.mlp_wgrad_planes((GPl[2 * l], GPl[2 * l + 1]), UP[l], P, outs[l], ins[l], sc[l], dyn)
+                if l < 8:
+                    w1 = w1 + ops.mlp_wgrad_planes(ZP[l], (XPl[2 * l], XPl[2 * l + 1]), P, outs[l], ins[l], sc[l], dyn2)
+                    db[l] = ops.colsum(Zb[l], outs[l]) * inv_dq
+                dW[l] = w1 * inv_dq
+        elif need_w:
             dW1, _ = mlp_bwd_weight(list(G), U, outs, ins, sc, dyn, want_bias=False)
             dW2, db2 = mlp_bwd_weight(Zb, list(act[:8]), outs[:8], ins[:8], sc[:8], dyn2, want_bias=True)
             for l in range(9):
@@ -212,10 +233,10 @@ def _plane_pair(rows, cols, dev, zero=False):
     return (mk((rows, cols), dtype=torch.float16, device=dev), mk((rows, cols), dtype=torch.float16, device=dev))
 
 
-def sdf_input_grad(x, g_sdf, g_feat, pe_w, act, Ws, bs):
+def sdf_input_grad(x, g_sdf, g_feat, pe_w, act, Ws, bs, xplanes=()):
     """dx of ImplicitNetwork as a twice-differentiable expression (the create_graph=True branch of
-    ops.SdfMlpTrainFunction.backward)."""
-    u0 = SdfMlpPeGradFunction.apply(x, g_sdf, g_feat, pe_w, *act, *Ws, *bs)
+    ops.SdfMlpTrainFunction.backward).  xplanes: the forward's layer-input planes (18 tensors) when it ran on planes."""
+    u0 = SdfMlpPeGradFunction.apply(x, g_sdf, g_feat, pe_w, *act, *Ws, *bs, *xplanes)
     return pe_vjp_torch(x, u0, pe_w, 6)
 
 

@@ -185,7 +185,7 @@ def test_translator_backward_matches_reference_autograd():
     x0 = torch.cat([tr.embed_fn(p.detach(), ratio_to_weights(6, 0.6)), conds.detach()[binds]], 1)
     X0 = torch.zeros((x0.shape[0], 168), device=DEV)
     X0[:, :167] = x0
-    _, acts = ops._plain_mlp_forward(X0, Ws, bs)                        # the same launches the Function's forward makes
+    _, acts, _ = ops._plain_mlp_forward(X0, Ws, bs)                      # the same launches the Function's forward makes
     pd, cd = p.detach().double().requires_grad_(True), conds.detach().double().requires_grad_(True)
     Wd = [w.double().requires_grad_(True) for w in Ws]
     bd = [b.double().requires_grad_(True) for b in bs]
