@@ -78,6 +78,22 @@ __device__ __forceinline__ float softplus100_fast(float z) {
   const float y = lg2_approx(1.f + ex2_approx(fminf(u, kUThr))) * 0.0069314718055994531f;
   return u > kUThr ? z : y;
 }
+// 256-bit global accesses (sm_100: LDG / STG .256).  A thread of the epilogue owns one output ROW, so a 128-bit store covers
+// half a 32-byte sector: the L2 then merges two partial writes per sector and, with ECC, fills the sector from DRAM first
+// (ncu: 33.5 M sector writes and 134 MB of DRAM reads beyond the operands per 131 k x 512 layer).  32 bytes per thread and
+// instruction = whole sectors.
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st_global_v8(__half* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
+               "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
 // 2-D tile load into this CTA's shared memory; completion bytes on a local mbarrier
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1) {
   asm volatile(
@@ -199,54 +215,77 @@ gemm3_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const bool fast = nb + 32 <= prm.split && nb + 32 <= prm.N && (prm.ldd & 3) == 0 &&
                           (prm.DH == nullptr || (prm.ldp & 7) == 0) &&
                           (fwd ? true : (prm.epi == TEPI_BWD_NONE || (prm.lde & 3) == 0));
+        // 256-bit accesses need 32-byte aligned rows (warp-uniform: pointers and strides only)
+        const bool wide = (prm.ldd & 7) == 0 && (reinterpret_cast<uintptr_t>(prm.D) & 31) == 0 &&
+                          (fwd ? (reinterpret_cast<uintptr_t>(prm.bias) & 31) == 0
+                               : (prm.epi == TEPI_BWD_NONE || ((prm.lde & 7) == 0 && (reinterpret_cast<uintptr_t>(prm.E) & 31) == 0)));
+        const bool wide_p = prm.DH != nullptr && (prm.ldp & 15) == 0 && (reinterpret_cast<uintptr_t>(prm.DH) & 31) == 0 &&
+                            (reinterpret_cast<uintptr_t>(prm.DL) & 31) == 0;
         if (fast) {
-          float4 ex[8];
+          float ex[32];
           const bool has_ex = fwd ? prm.bias != nullptr : prm.epi != TEPI_BWD_NONE;
           const bool row_ok = m < prm.M;
           if (has_ex) {
-            const float4* src = reinterpret_cast<const float4*>(fwd ? prm.bias + nb
-                                                                    : prm.E + (long long)(row_ok ? m : 0) * prm.lde + nb);
+            const float* src = fwd ? prm.bias + nb : prm.E + (long long)(row_ok ? m : 0) * prm.lde + nb;
+            if (wide) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ex[j] = __ldg(src + j);
+              for (int j = 0; j < 4; ++j) ld_global_nc_v8(src + 8 * j, ex + 8 * j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(src) + j);
+                ex[4 * j] = t.x; ex[4 * j + 1] = t.y; ex[4 * j + 2] = t.z; ex[4 * j + 3] = t.w;
+              }
+            }
           }
           tmem_ld_wait();
           float o[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float e4[4] = {ex[j].x, ex[j].y, ex[j].z, ex[j].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float v = __uint_as_float(r[4 * j + e]) * unscale;
-              if (fwd) {
-                if (has_ex) v += e4[e];
-                if (prm.epi == TEPI_FWD_SOFTPLUS100) v = softplus100_fast(v);
-                else if (prm.epi == TEPI_FWD_RELU) v = fmaxf(v, 0.f);
-              } else if (prm.epi == TEPI_BWD_SOFTPLUS100) {
-                v *= 1.f - ex2_approx(-kSoftplusLog2Scale * e4[e]);
-              } else if (prm.epi == TEPI_BWD_RELU) {
-                v = e4[e] > 0.f ? v : 0.f;
-              }
-              o[4 * j + e] = v;
+          for (int e = 0; e < 32; ++e) {
+            float v = __uint_as_float(r[e]) * unscale;
+            if (fwd) {
+              if (has_ex) v += ex[e];
+              if (prm.epi == TEPI_FWD_SOFTPLUS100) v = softplus100_fast(v);
+              else if (prm.epi == TEPI_FWD_RELU) v = fmaxf(v, 0.f);
+            } else if (prm.epi == TEPI_BWD_SOFTPLUS100) {
+              v *= 1.f - ex2_approx(-kSoftplusLog2Scale * ex[e]);
+            } else if (prm.epi == TEPI_BWD_RELU) {
+              v = ex[e] > 0.f ? v : 0.f;
             }
+            o[e] = v;
           }
           if (row_ok) {
-            float4* d = reinterpret_cast<float4*>(prm.D + (long long)m * prm.ldd + nb);
+            float* d = prm.D + (long long)m * prm.ldd + nb;
+            if (wide) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) d[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) st_global_v8(d + 8 * j, o + 8 * j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(d)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
           }
           if (prm.DH && row_ok) {
-            uint4* dh = reinterpret_cast<uint4*>(prm.DH + (long long)m * prm.ldp + nb);
-            uint4* dl = reinterpret_cast<uint4*>(prm.DL + (long long)m * prm.ldp + nb);
+            __half* dh = prm.DH + (long long)m * prm.ldp + nb;
+            __half* dl = prm.DL + (long long)m * prm.ldp + nb;
 #pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              float v[8];
+            for (int j16 = 0; j16 < 2; ++j16) {
+              uint4 hi[2], lo[2];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = o[8 * j8 + e] * pscale;
-              range_check8(v, prm.status, 3500);
-              uint4 hi, lo;
-              split8(v, hi, lo);
-              dh[j8] = hi;
-              dl[j8] = lo;
+              for (int h = 0; h < 2; ++h) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = o[16 * j16 + 8 * h + e] * pscale;
+                range_check8(v, prm.status, 3500);
+                split8(v, hi[h], lo[h]);
+              }
+              if (wide_p) {
+                st_global_v8(dh + 16 * j16, hi[0], hi[1]);
+                st_global_v8(dl + 16 * j16, lo[0], lo[1]);
+              } else {
+                reinterpret_cast<uint4*>(dh + 16 * j16)[0] = hi[0]; reinterpret_cast<uint4*>(dh + 16 * j16)[1] = hi[1];
+                reinterpret_cast<uint4*>(dl + 16 * j16)[0] = lo[0]; reinterpret_cast<uint4*>(dl + 16 * j16)[1] = lo[1];
+              }
             }
           }
         } else {
