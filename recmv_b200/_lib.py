@@ -6,8 +6,8 @@ FastMinv/M3x3Inv.cpp:4-6).
 """
 import ctypes
 import os
-from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
-                    c_uint8, c_void_p)
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size_t,
+                    c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librecmv_b200.so")

@@ -12,7 +12,6 @@ Paths:
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import ops
 from .Embedder import get_embedder, ratio_to_weights

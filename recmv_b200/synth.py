@@ -2,7 +2,6 @@
 diffused skinning voxel, poses, pinhole rays, SDF grids for marching cubes.  Pure torch; used by
 bench.py, the tests and the golden-vector generator (there is no network for datasets/checkpoints).
 """
-import math
 
 import torch
 
