@@ -82,8 +82,10 @@ __device__ __forceinline__ float softplus100_fast(float z) {
 // half a 32-byte sector: the L2 then merges two partial writes per sector and, with ECC, fills the sector from DRAM first
 // (ncu: 33.5 M sector writes and 134 MB of DRAM reads beyond the operands per 131 k x 512 layer).  32 bytes per thread and
 // instruction = whole sectors.
+// .cs (evict-first): the fp32 copy of a layer's output is not read again before the backward pass -- it should not push the
+// operand planes (re-read by the other column tiles, and by the next layer) out of L2
 __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
                "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 __device__ __forceinline__ void st_global_v8(__half* p, uint4 a, uint4 b) {
