@@ -576,6 +576,11 @@ def weight_planes(W, transpose=False):
     operand), computed once per tensor OBJECT and version: the forward, the reverse chain and the two second-order passes of
     one training step all see the same weight tensor, so three of four splits are cache hits.  The cache lives on the tensor
     (an attribute), so it dies with it -- no address-keyed table that could go stale."""
+    if W.is_leaf:
+        # a Parameter can be rewritten through `.data` without a version bump: never cache on leaves (weight-normed layers
+        # hand over a fresh non-leaf W = g v / |v| every forward, which is the case the cache is for)
+        Wd = W.detach().contiguous().float()
+        return split_planes(Wd, Wd.shape[0], Wd.shape[1], 1024.0, transpose=transpose)
     ver = W._version
     cache = getattr(W, "_recmv_planes", None)
     if cache is None or cache[0] != ver:
