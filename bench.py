@@ -244,7 +244,7 @@ def secondary_rates(dev, ren, mode):
                 "algorithmic_tflops": flop_per_point * P / (ms * 1e-3) / 1e12}
 
     # training step of the SDF network on the same engine: fused forward that saves the layer inputs + tcgen05 backward
-    # GEMMs (backward-data per layer, ONE weight-gradient launch) behind loss.backward(); ALGORITHMIC FLOP per point =
+    # GEMMs (backward-data and weight gradient per layer, all on the operand planes) behind loss.backward(); ALGORITHMIC FLOP per point =
     # 3 x 3 933 184 (forward, backward-data, weight gradient), each issued as 3 fp16 MMAs per product
     Pt = 1 << 17
     xt = pts[:Pt].clone()
@@ -275,7 +275,7 @@ def secondary_rates(dev, ren, mode):
                 "backward": ops.SdfMlpTrainFunction.last_backward, "algorithmic_tflops": tf,
                 "roofline": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                              "mma_passes": 3, "issued_frac": 3 * tf / peak_tf},
-                "includes": "weight-norm graph, cotangent packing, 9 backward-data launches, 1 weight-gradient launch, "
+                "includes": "weight-norm graph, cotangent packing, 9 backward-data launches, 9 weight-gradient launches + bias column sums, "
                             "PE Jacobian, autograd bookkeeping (everything loss.backward() runs)"}
     train = rate_train()
     # the same step through torch autograd over cuBLAS fp32 (what the reference runs): informative, same GPU, same run

@@ -718,7 +718,7 @@ class SdfMlpTrainFunction(torch.autograd.Function):
               (The inference engine keeps activations on-chip; a variant of it that also streamed them to HBM was
               built and dropped: it fails above ~50 k points per call, profiles/r02_notes.md.)
     backward: first order (`loss.backward()`, parameter VJPs of propagateTmpPsGrad) -> 9 backward-data launches +
-              ONE weight-gradient launch + the PE Jacobian; weight-norm's (g, v) and anything upstream of x stay
+              nine weight-gradient launches on the same operand planes (recmv_mlp_wgrad_planes) + the PE Jacobian; weight-norm's (g, v) and anything upstream of x stay
               ordinary autograd.  Called with create_graph=True (eikonal / normals, network.py:121-133) the backward
               instead re-runs the network as a torch graph over the saved inputs -- twice differentiable, on cuBLAS;
               `last_backward` says which ran."""
