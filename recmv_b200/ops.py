@@ -717,11 +717,12 @@ class SdfMlpTrainFunction(torch.autograd.Function):
               concatenation is a column range of layer 4's input buffer, its 1/sqrt2 a scale of that layer's GEMM.
               (The inference engine keeps activations on-chip; a variant of it that also streamed them to HBM was
               built and dropped: it fails above ~50 k points per call, profiles/r02_notes.md.)
-    backward: first order (`loss.backward()`, parameter VJPs of propagateTmpPsGrad) -> 9 backward-data launches +
-              nine weight-gradient launches on the same operand planes (recmv_mlp_wgrad_planes) + the PE Jacobian; weight-norm's (g, v) and anything upstream of x stay
-              ordinary autograd.  Called with create_graph=True (eikonal / normals, network.py:121-133) the backward
-              instead re-runs the network as a torch graph over the saved inputs -- twice differentiable, on cuBLAS;
-              `last_backward` says which ran."""
+    backward: first order (`loss.backward()`, parameter VJPs of propagateTmpPsGrad) -> 9 backward-data launches + nine
+              weight-gradient launches on the same operand planes (recmv_mlp_wgrad_planes) + the PE Jacobian; weight-norm's
+              (g, v) and anything upstream of x stay ordinary autograd.  Called with create_graph=True for the INPUT gradient
+              (eikonal / normals, network.py:121-133, inside ops.input_grad_only()) the backward returns the reverse chain as
+              a differentiable op on the same GEMMs (recmv_b200/second_order.py); a create_graph call that also wants
+              parameter gradients with a graph re-runs the network as a torch graph (cuBLAS); `last_backward` says which ran."""
     last_backward = None
 
     @staticmethod
