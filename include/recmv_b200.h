@@ -225,13 +225,15 @@ RECMV_API int recmv_mlp_layer_planes(const void* a_hi, const void* a_lo, int64_t
 
 /* Weight gradient from the same planes, no transposed copies (tcgen05 reads the row-major planes as MN-major operands):
  *   dW [out_dim][in_dim] = scale * G^T X,  g planes [P][ldg_p] = 64 * dyn * g (columns < out_dim), x planes [P][ldx_p] = 64 * x.
- * The sample range is split over the SMs, partial tiles are summed in a fixed order (deterministic).  workspace: device fp32,
- * recmv_mlp_wgrad_workspace_floats() elements, reusable across calls on one stream.
+ * The sample range is split over the SMs, partial tiles are summed in a fixed order (deterministic).  db [out_dim] (optional)
+ * = sum_p g[p][:] = the bias gradient, from one more product of the G tiles with a tile of ones in the same launch.  workspace:
+ * device fp32, recmv_mlp_wgrad_workspace_floats() elements, reusable across calls on one stream.
  *   recmv_colsum: out[c] = sum_r g[r][c] (the bias gradient from the fp32 cotangent); partial = scratch of 128 * cols floats. */
 RECMV_API size_t recmv_mlp_wgrad_workspace_floats(void);
 RECMV_API int recmv_mlp_wgrad_planes(const void* g_hi, const void* g_lo, int64_t ldg_p, const void* x_hi, const void* x_lo,
                                      int64_t ldx_p, int64_t P, int out_dim, int in_dim, float scale,
-                                     const float* dyn_scale /*device*/, float* workspace, float* dW, recmv_stream_t stream);
+                                     const float* dyn_scale /*device*/, float* workspace, float* dW, float* db /*or NULL*/,
+                                     recmv_stream_t stream);
 RECMV_API int recmv_colsum(const float* g, int64_t ld, int64_t rows, int cols, float* partial, float* out,
                            recmv_stream_t stream);
 /* (f4) element-wise steps of the second-order pass between two plane GEMMs (recmv_b200/second_order.py), each one launch that

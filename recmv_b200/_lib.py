@@ -103,7 +103,7 @@ SIGNATURES = {
     "recmv_c2f_todo_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "recmv_mlp_wgrad_workspace_floats": (c_size_t, []),
     "recmv_mlp_wgrad_planes": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_float,
-                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "recmv_colsum": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "recmv_softplus_tangent_planes": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float,
                                               c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),

@@ -380,10 +380,18 @@ gemm3_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 // short, gemm3.cu); partial tiles go to a workspace and are summed in split order by a second launch (deterministic).
 struct WgParams {
   float* ws;                 // [splits][tiles_m * 128][tiles_n * 128] raw partial sums (accumulator units, gain applied)
+  float* ws_db;              // [splits][tiles_m * 128] raw partial row sums of A (the bias gradient), or NULL
   long long nkb;             // ceil(P / 64)
   int M, N, tiles_m, tiles_n, splits, chunk_kb;
   DevStatus* status;
 };
+
+// Bias gradient for free: db[m] = sum_p G[p][m] is one more product of the A tile, with a [16 x 64] tile of ones as a K-major B
+// operand (2 KB of shared memory, written once per CTA): 8 extra N = 16 MMAs per K block in the CTAs of the first column of
+// tiles, accumulated in 16 more TMEM columns per buffer and chunk-summed by the same epilogue warps.
+constexpr uint32_t kOffOnes = (kOffMisc + 64 + 1023u) & ~1023u;
+constexpr uint32_t kSmemBytesWg = kOffOnes + 2048 + 1024 /* alignment slack */;
+constexpr uint32_t kDbCol = 2 * kBN;               // TMEM columns [256, 288): two 16-column accumulators
 
 __device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
@@ -406,6 +414,13 @@ gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   const long long kb0 = prm.nkb * split / prm.splits, kb1 = prm.nkb * (split + 1) / prm.splits;
   const long long nchunks = (kb1 - kb0 + prm.chunk_kb - 1) / prm.chunk_kb;
 
+  // every CTA of a tile row does the bias-gradient product for the K blocks kb with kb % tiles_n == tn (spreading the extra
+  // MMAs over the row's CTAs: with all of them on the tn == 0 CTAs the launch took 185 instead of 135 us)
+  const bool with_db = prm.ws_db != nullptr;
+  auto db_blocks = [&](long long c0, long long c1) {   // number of K blocks of [c0, c1) this CTA owns for the bias gradient
+    const long long first = c0 + ((tn - c0 % prm.tiles_n) + prm.tiles_n) % prm.tiles_n;
+    return first < c1 ? (c1 - first + prm.tiles_n - 1) / prm.tiles_n : 0LL;
+  };
   if (threadIdx.x == 0) {
     *abort_flag = 0;
     for (int s = 0; s < kStages; ++s) { mbar_init(BAR(kBarFull + s), 1); mbar_init(BAR(kBarEmpty + s), 1); }
@@ -413,8 +428,12 @@ gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     fence_mbar_init();
     prefetch_tmap(&tm_a_hi); prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_b_hi); prefetch_tmap(&tm_b_lo);
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {    // the ones tile: 128 x 16 bytes of fp16 1.0 (layout-free: all equal)
+    *reinterpret_cast<uint4*>(gbase + kOffOnes + 16 * (threadIdx.x - 64)) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async();
+  }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -448,6 +467,8 @@ gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_f16(kBM, kBN) | (1u << 15) | (1u << 16);   // A and B MN-major
+      const uint32_t idesc_db = idesc_f16(kBM, 16) | (1u << 15);               // A MN-major, B (ones) K-major
+      const uint64_t ones = smem_desc_sw128(base + kOffOnes);
       long long kbg = 0;
       for (long long ch = 0; ch < nchunks; ++ch) {
         const int buf = (int)(ch & 1);
@@ -455,6 +476,7 @@ gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         tc_fence_after();
         const uint32_t dcol = tmem_base + (uint32_t)(buf * kBN);
         const long long c0 = kb0 + ch * prm.chunk_kb, c1 = c0 + prm.chunk_kb < kb1 ? c0 + prm.chunk_kb : kb1;
+        bool db_started = false;
         for (long long kb = c0; kb < c1; ++kb, ++kbg) {
           const int s = (int)(kbg % kStages);
           mbar_wait(BAR(kBarFull + s), (uint32_t)((kbg / kStages) & 1), abort_flag, prm.status, 3950 + s);
@@ -468,6 +490,14 @@ gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
           for (int k = 0; k < 4; ++k) umma_f16_1cta(dcol, a_hi + 128 * k, b_lo + 128 * k, idesc, 1u);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16_1cta(dcol, a_hi + 128 * k, b_hi + 128 * k, idesc, 1u);
+          if (with_db && kb % prm.tiles_n == tn) {
+            const uint32_t dbcol = tmem_base + kDbCol + (uint32_t)(buf * 16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_1cta(dbcol, a_lo + 128 * k, ones + 2 * k, idesc_db, (!db_started && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_1cta(dbcol, a_hi + 128 * k, ones + 2 * k, idesc_db, 1u);
+            db_started = true;
+          }
           umma_commit_1cta(BAR(kBarEmpty + s));
         }
         umma_commit_1cta(BAR(kBarAccFull + buf));
@@ -479,6 +509,8 @@ gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     float acc[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    float dbacc = 0.f;
+    const bool db_warp = with_db && cg == 0;          // warp-uniform
     for (long long ch = 0; ch < nchunks; ++ch) {
       const int buf = (int)(ch & 1);
       const long long c0 = kb0 + ch * prm.chunk_kb;
@@ -491,6 +523,13 @@ gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = fmaf(__uint_as_float(r[j]), gain, acc[j]);
+      const long long nb_db = db_warp ? db_blocks(c0, c0 + len) : 0;      // warp-uniform
+      if (nb_db > 0) {
+        uint32_t rb[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kDbCol + (uint32_t)(buf * 16), rb);
+        tmem_ld_wait();
+        dbacc = fmaf(__uint_as_float(rb[0]), acc_trunc_gain((int)nb_db), dbacc);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_local(BAR(kBarAccEmpty + buf));
@@ -500,6 +539,7 @@ gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4)
       *reinterpret_cast<float4*>(d + 4 * j4) = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+    if (db_warp) prm.ws_db[((long long)split * prm.tiles_n + tn) * prm.tiles_m * kBM + tm * kBM + row] = dbacc;
   }
 
   __syncwarp();
@@ -507,7 +547,7 @@ gemm3_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -526,6 +566,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     for (int k = 0; k < splits; ++k) a += ws[k * split_stride + m * ldw + n];
     dW[m * ldd + n] = a * s;
   }
+}
+
+// db[m] = (1 / (64 dyn)) * sum over splits of the partial row sums
+__global__ void __launch_bounds__(256) wgrad_reduce_db_kernel(const float* __restrict__ ws_db, int splits, long long split_stride,
+                                                              int M, const float* __restrict__ dyn_scale, float* __restrict__ db) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float a = 0.f;
+  for (int k = 0; k < splits; ++k) a += ws_db[k * split_stride + m];
+  db[m] = a / (64.f * (dyn_scale ? __ldg(dyn_scale) : 1.f));
 }
 
 // column sums of an fp32 matrix (bias gradient), two deterministic stages: partial[rs][c] over row slab rs, then the slabs
@@ -802,17 +852,21 @@ extern "C" int recmv_mlp_layer_planes(const void* a_hi, const void* a_lo, int64_
 extern "C" size_t recmv_mlp_wgrad_workspace_floats(void) {
   int dev = 0;
   cudaGetDevice(&dev);
-  return (size_t)(num_sms() + 16) * kBM * kBN;
+  return (size_t)(num_sms() + 16) * (kBM * kBN + kBM);   // tiles x splits <= SMs partial tiles + as many partial row sums
 }
 
 extern "C" int recmv_mlp_wgrad_planes(const void* g_hi, const void* g_lo, int64_t ldg_p, const void* x_hi, const void* x_lo,
                                       int64_t ldx_p, int64_t P, int out_dim, int in_dim, float scale, const float* dyn_scale,
-                                      float* workspace, float* dW, recmv_stream_t stream) {
+                                      float* workspace, float* dW, float* db, recmv_stream_t stream) {
   if (P < 0 || out_dim <= 0 || in_dim <= 0) return RECMV_E_SHAPE;
   if (!g_hi || !g_lo || !x_hi || !x_lo || !workspace || !dW) return RECMV_E_NULL;
   if (P > (int64_t)1 << 30) return RECMV_E_RANGE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (P == 0) return (int)cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)out_dim * in_dim, st);
+  if (P == 0) {
+    cudaError_t e0 = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)out_dim * in_dim, st);
+    if (e0 == cudaSuccess && db) e0 = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)out_dim, st);
+    return (int)e0;
+  }
   CUtensorMap ta_h, ta_l, tb_h, tb_l;
   int s = make_plane_tmap(&ta_h, g_hi, (uint64_t)out_dim, (uint64_t)P, (uint64_t)ldg_p, 64);
   if (!s) s = make_plane_tmap(&ta_l, g_lo, (uint64_t)out_dim, (uint64_t)P, (uint64_t)ldg_p, 64);
@@ -826,7 +880,7 @@ extern "C" int recmv_mlp_wgrad_planes(const void* g_hi, const void* g_lo, int64_
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_done[dev & 15]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWg);
     if (e != cudaSuccess) return (int)e;
     attr_done[dev & 15] = true;
   }
@@ -842,12 +896,17 @@ extern "C" int recmv_mlp_wgrad_planes(const void* g_hi, const void* g_lo, int64_
   prm.splits = splits;
   prm.chunk_kb = 32;
   prm.status = (DevStatus*)sd;
-  gemm3_wgrad_kernel<<<tiles * splits, kThreads, kSmemBytes, st>>>(ta_h, ta_l, tb_h, tb_l, prm);
+  const long long db_stride = (long long)prm.tiles_m * kBM;
+  prm.ws_db = db ? workspace + (size_t)splits * prm.tiles_m * kBM * prm.tiles_n * kBN : nullptr;
+  gemm3_wgrad_kernel<<<tiles * splits, kThreads, kSmemBytesWg, st>>>(ta_h, ta_l, tb_h, tb_l, prm);
   s = launch_status();
   if (s) return s;
   const long long ldw = (long long)prm.tiles_n * kBN, split_stride = (long long)prm.tiles_m * kBM * ldw;
   wgrad_reduce_kernel<<<stride_grid((int64_t)out_dim * in_dim, 256, 4), 256, 0, st>>>(
       workspace, splits, split_stride, ldw, out_dim, in_dim, scale / (64.f * 64.f), dyn_scale, dW, in_dim);
+  s = launch_status();
+  if (s || !db) return s;
+  wgrad_reduce_db_kernel<<<(out_dim + 255) / 256, 256, 0, st>>>(prm.ws_db, splits * prm.tiles_n, db_stride, out_dim, dyn_scale, db);
   return launch_status();
 }
 

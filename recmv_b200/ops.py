@@ -631,18 +631,20 @@ def _wgrad_workspace(dev):
     return _WGRAD_WS[key]
 
 
-def mlp_wgrad_planes(g_planes, x_planes, P, out_dim, in_dim, scale=1.0, dyn=None):
-    """dW [out_dim, in_dim] = scale * G^T X from the operand planes the layer GEMMs wrote (recmv_mlp_wgrad_planes)."""
+def mlp_wgrad_planes(g_planes, x_planes, P, out_dim, in_dim, scale=1.0, dyn=None, want_bias=False):
+    """dW [out_dim, in_dim] = scale * G^T X from the operand planes the layer GEMMs wrote (recmv_mlp_wgrad_planes); with
+    want_bias also db [out_dim] = sum over samples of g (same launch) -> (dW, db)."""
     gh, gl = g_planes
     xh, xl = x_planes
     dev = gh.device
     ws, _ = _wgrad_workspace(dev)
     dW = torch.empty((out_dim, in_dim), dtype=torch.float32, device=dev)
+    db = torch.empty((out_dim,), dtype=torch.float32, device=dev) if want_bias else None
     with torch.cuda.device(dev):
         check(_lib.load().recmv_mlp_wgrad_planes(_ptr(gh), _ptr(gl), gh.stride(0), _ptr(xh), _ptr(xl), xh.stride(0), int(P),
-                                                 int(out_dim), int(in_dim), float(scale), _ptr(dyn), _ptr(ws), _ptr(dW),
+                                                 int(out_dim), int(in_dim), float(scale), _ptr(dyn), _ptr(ws), _ptr(dW), _ptr(db),
                                                  _stream(gh)), "recmv_mlp_wgrad_planes")
-    return dW
+    return (dW, db) if want_bias else dW
 
 
 def colsum(G, cols):
@@ -845,8 +847,8 @@ class SdfMlpTrainFunction(torch.autograd.Function):
             # weight gradient straight from the planes both passes wrote (MN-major operands, no transposed copies)
             xpl = saved[28:46]
             for l in range(9):
-                dW[l] = mlp_wgrad_planes(GP[l], (xpl[2 * l], xpl[2 * l + 1]), P, outs[l], ins[l], _INV_SQRT2 if l == 4 else 1.0, dyn)
-                db[l] = colsum(G[l], outs[l])
+                dW[l], db[l] = mlp_wgrad_planes(GP[l], (xpl[2 * l], xpl[2 * l + 1]), P, outs[l], ins[l],
+                                                _INV_SQRT2 if l == 4 else 1.0, dyn, want_bias=True)
         elif need_w:
             dW, db = mlp_bwd_weight(G, list(act), outs, ins, [_INV_SQRT2 if l == 4 else 1.0 for l in range(9)], dyn)
         return (dx, None, None, None, *dW, *db)
@@ -916,8 +918,7 @@ def _plain_mlp_backward(g_out, Ws, acts, need_w, need_x0, xplanes=()):
     if need_w and planes and len(xplanes) == 2 * n:
         for l in range(n):
             o, i = Ws[l].shape
-            dW[l] = mlp_wgrad_planes(GP[l], (xplanes[2 * l], xplanes[2 * l + 1]), P, o, i, 1.0, dyn)
-            db[l] = colsum(G[l], o)
+            dW[l], db[l] = mlp_wgrad_planes(GP[l], (xplanes[2 * l], xplanes[2 * l + 1]), P, o, i, 1.0, dyn, want_bias=True)
     elif need_w:
         dW, db = mlp_bwd_weight(G, list(acts), [w.shape[0] for w in Ws], [w.shape[1] for w in Ws], None, dyn)
     return dX0, dW, db

@@ -211,8 +211,9 @@ def _sdf_backward_planes(ctx, q, x, dyn, act, Ws, G, outs, ins, need, need_x, ne
             for l in range(9):
                 w1 = ops.mlp_wgrad_planes((GPl[2 * l], GPl[2 * l + 1]), UP[l], P, outs[l], ins[l], sc[l], dyn)
                 if l < 8:
-                    w1 = w1 + ops.mlp_wgrad_planes(ZP[l], (XPl[2 * l], XPl[2 * l + 1]), P, outs[l], ins[l], sc[l], dyn2)
-                    db[l] = ops.colsum(Zb[l], outs[l]) * inv_dq
+                    w2, b2 = ops.mlp_wgrad_planes(ZP[l], (XPl[2 * l], XPl[2 * l + 1]), P, outs[l], ins[l], sc[l], dyn2, want_bias=True)
+                    w1 = w1 + w2
+                    db[l] = b2 * inv_dq
                 dW[l] = w1 * inv_dq
         elif need_w:
             dW1, _ = mlp_bwd_weight(list(G), U, outs, ins, sc, dyn, want_bias=False)

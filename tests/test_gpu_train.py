@@ -254,10 +254,14 @@ def test_wgrad_on_planes_matches_fp64(P, out_dim, in_dim):
     dyn = ops.grad_dyn_scale(G)
     gp = ops.split_planes(G, P, out_dim, 64.0, scale_dev=dyn, ldp=512)
     xp = ops.split_planes(X, P, in_dim, 64.0, ldp=512)
-    dW = ops.mlp_wgrad_planes(gp, xp, P, out_dim, in_dim, 0.5, dyn)
+    dW, db_mma = ops.mlp_wgrad_planes(gp, xp, P, out_dim, in_dim, 0.5, dyn, want_bias=True)
     ref = 0.5 * G[:, :out_dim].double().T @ X[:, :in_dim].double()
     e = merr(dW, ref)
+    assert torch.equal(dW, ops.mlp_wgrad_planes(gp, xp, P, out_dim, in_dim, 0.5, dyn))      # deterministic, with or without db
     db = ops.colsum(G, out_dim)
-    eb = merr(db, G[:, :out_dim].double().sum(0))
-    print(f"wgrad planes P={P} {out_dim}x{in_dim}: {e:.2e}  colsum {eb:.2e}")
+    ref_b = G[:, :out_dim].double().sum(0)
+    eb = merr(db, ref_b)
+    ebm = merr(db_mma, ref_b)
+    print(f"wgrad planes P={P} {out_dim}x{in_dim}: {e:.2e}  colsum {eb:.2e}  bias gradient from the ones tile {ebm:.2e}")
+    assert ebm < 5e-6
     assert e < (6e-6 if P > 10000 else 3e-6) and eb < 2e-6      # measured 3.3e-6 at 70 000 samples
